@@ -1,0 +1,124 @@
+/* merlin_b200.h -- C ABI of the B200-native MERLIN rollout hot path (libmerlin_b200.so).
+ *
+ * The reference (borangundogan/PPO-2DGrid) has no FFI layer: its boundary for this path is the
+ * Python API of gymnasium/minigrid environments.  Each entry point below states which reference
+ * call it replaces (file:line are relative to the reference checkout):
+ *
+ *   merlin_env_create / destroy   gym.make(env_id, size=...) + wrapper stack
+ *                                 src/scenario_creator/scenario_creator.py:35-57 ; constants from
+ *                                 src/custom_envs/base_env.py:32-41 (max_steps = 4*size^2, view 7)
+ *   merlin_env_upload_layouts     the result of MiniGridEnv.reset() -> _gen_grid()
+ *                                 src/custom_envs/medium_hard_env.py:12-45 (and the four siblings)
+ *   merlin_env_set_tile_atlas     Grid.render_tile cache used by RGBImgPartialObsWrapper
+ *                                 (src/scenario_creator/scenario_creator.py:48, tile_size 8)
+ *   merlin_env_reset              env.reset()   src/ppo.py:35,65,96 ; src/fomaml.py:63,92,184
+ *   merlin_env_step               env.step(a)   src/ppo.py:76 ; src/fomaml.py:71 -- through
+ *                                 ThreeActionWrapper (src/wrappers/three_action_wrapper.py:10-17),
+ *                                 optionally StuckPenaltyWrapper (src/wrappers/stuck_penalty_wrapper.py:29-58)
+ *   merlin_gae                    PPO.compute_gae src/ppo.py:107-120 ; FOMAML src/fomaml.py:116-123
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative MERLIN_E* code on failure;
+ *     merlin_last_error() returns a thread-local message for the last failure.
+ *   - All data pointers passed to reset/step/gae are CALLER-OWNED DEVICE pointers on the handle's
+ *     device; the library neither frees nor retains them.  Upload functions take HOST pointers
+ *     and copy.  Env state lives in device memory owned by the handle.
+ *   - reset/step/gae are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream), allocate nothing, never synchronise, and may be captured in a CUDA graph.
+ *   - A handle is not thread-safe; one caller thread per handle.  One handle per device.
+ *   - There is no CPU fallback: without a CUDA device every entry point fails with MERLIN_ECUDA.
+ *
+ * Packed cell code (1 byte per grid cell, row-major [y*W + x]):
+ *   bits 3..0  type: minigrid OBJECT_TO_IDX (1 empty, 2 wall, 3 floor, 4 door OPEN, 5 key, 6 ball,
+ *                    7 box, 8 goal, 9 lava) plus 11 = door CLOSED, 12 = door LOCKED
+ *   bits 6..4  colour: minigrid COLOR_TO_IDX (0 red 1 green 2 blue 3 purple 4 yellow 5 grey)
+ *   merlin_pack_cell(type, color, state) converts one minigrid (type, color, state) triple.
+ */
+#ifndef MERLIN_B200_H
+#define MERLIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MERLIN_OK 0
+#define MERLIN_EINVAL (-1)   /* bad argument */
+#define MERLIN_ECUDA (-2)    /* CUDA runtime / launch failure, or no device */
+#define MERLIN_ESTATE (-3)   /* call out of order (e.g. step before layouts were uploaded) */
+#define MERLIN_ENOMEM (-4)
+
+/* flags for merlin_env_create */
+#define MERLIN_F_AUTO_RESET 0x1u      /* finished envs restart inside step(); obs is the new episode's */
+#define MERLIN_F_RESET_SAME 0x2u      /* restart on the SAME layout (FOMAML, src/fomaml.py:92); default: advance cursor by n_envs */
+#define MERLIN_F_SEVEN_ACTIONS 0x4u   /* full MiniGrid action set 0..6; default: ThreeActionWrapper {left,right,forward} */
+#define MERLIN_F_STUCK_PENALTY 0x8u   /* StuckPenaltyWrapper semantics (off in the reference's training path) */
+#define MERLIN_F_EXPLORE_BONUS 0x10u  /* first-visit-per-episode bonus (not in the reference; builder-specified) */
+
+typedef struct merlin_env merlin_env_t;
+
+typedef struct merlin_env_config {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n_envs;          /* N >= 1 */
+  int32_t width, height;   /* grid W,H in [3,255] */
+  int32_t max_steps;       /* episode cap; 0 => 4*W*H (src/custom_envs/base_env.py:32-33) */
+  int32_t view;            /* agent_view_size; only 7 is built */
+  int32_t tile;            /* RGB tile size in pixels; only 8 is built */
+  uint32_t flags;          /* MERLIN_F_* */
+  int32_t stuck_max_stay;  /* default 3  (stuck_penalty_wrapper.py:12) */
+  double stuck_penalty;    /* default -0.1 */
+  double explore_bonus;    /* used when MERLIN_F_EXPLORE_BONUS */
+} merlin_env_config_t;
+
+/* Optional outputs of step(); any pointer may be NULL. */
+typedef struct merlin_step_extras {
+  float* episode_return;   /* [N] sum of rewards of the episode that ended this step, else 0 */
+  int32_t* episode_length; /* [N] its length, else 0 */
+  uint8_t* stuck;          /* [N] info["stuck"] of StuckPenaltyWrapper */
+} merlin_step_extras_t;
+
+void merlin_env_default_config(merlin_env_config_t* cfg);
+int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out);
+int merlin_env_destroy(merlin_env_t* h);
+
+/* HOST inputs. cells: [n_layouts][H*W] packed codes; agent_xyd: [n_layouts][3] = x, y, dir. Replaces the pool. */
+int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32_t* agent_xyd, int32_t n_layouts);
+/* HOST input. tiles: [128][tile*tile*3] u8, indexed by packed code (0 = unseen cell, 10 = agent on empty,
+ * 13/14/15 | colour<<4 = agent carrying key/ball/box). Required before an RGB observation is requested. */
+int merlin_env_set_tile_atlas(merlin_env_t* h, const uint8_t* tiles, int32_t n_tiles);
+/* HOST input or NULL. cursor[e] = pool index env e loads at its next reset. Default e % n_layouts. */
+int merlin_env_set_cursors(merlin_env_t* h, const int32_t* cursor);
+
+/* (Re)start envs. mask: DEVICE u8[N] or NULL (= all). obs_rgb: DEVICE u8[N][56][56][3] or NULL;
+ * obs_sym: DEVICE u8[N][7][7][3] or NULL. Only restarted envs have their observation rows written. */
+int merlin_env_reset(merlin_env_t* h, const uint8_t* mask, uint8_t* obs_rgb, uint8_t* obs_sym, void* stream);
+
+/* One step of every env. actions: DEVICE i64[N]. reward f32[N], terminated/truncated u8[N] required.
+ * Out-of-range actions are executed as `done` (no-op) and counted (merlin_env_bad_actions). */
+int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
+                    uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream);
+
+/* State views: DEVICE pointers owned by the handle (valid until destroy). */
+int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state_xyds /* int4[N]: pose,step_count,cursor,stuck */,
+                          uint8_t** cells /* [N][cell_stride] or NULL when grids are immutable */,
+                          int32_t* cell_stride, float** episode_return);
+/* Synchronous copy of the env state to HOST buffers (any may be NULL): state i32[N][4], cells u8[N][H*W]
+ * (fails with MERLIN_ESTATE when grids are immutable -- index the pool by state[e][2] instead), episode_return f32[N]. */
+int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float* episode_return);
+int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count); /* synchronises the device */
+int64_t merlin_env_launch_count(merlin_env_t* h);             /* kernels launched so far by this handle */
+
+/* GAE + returns over a time-major [T][N] rollout (all DEVICE f32). done = terminated|truncated as 0/1.
+ * adv[t] = delta_t + gamma*lam*(1-done_t)*adv[t+1]; ret = val + adv.  fp32, unfused, reference op order. */
+int merlin_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv, float* ret,
+               int32_t T, int32_t N, double gamma, double lam, void* stream);
+
+uint8_t merlin_pack_cell(int type, int color, int state);
+const char* merlin_last_error(void);
+const char* merlin_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERLIN_B200_H */

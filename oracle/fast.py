@@ -113,7 +113,9 @@ class OracleVecEnv:
         self.atlas = atlas or TileAtlas(tile)
         if want_rgb:
             trip = np.unique(enc.reshape(-1, 3), axis=0)
-            self.atlas.ensure([tuple(x) for x in trip])
+            need = {tuple(int(v) for v in x) for x in trip}
+            need |= {(4, c, st) for (t, c, _s) in list(need) if t == 4 for st in (0, 1, 2)}  # toggling changes door state
+            self.atlas.ensure(sorted(need))
         N, HW = self.N, self.W * self.H
         self.gt = np.ones((N, HW), np.uint8)
         self.gc = np.zeros((N, HW), np.uint8)

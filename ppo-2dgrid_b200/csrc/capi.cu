@@ -1,0 +1,311 @@
+// capi.cu -- the C ABI declared in include/merlin_b200.h: handle lifetime, host->device uploads,
+// argument validation and kernel launches.  No compute happens on the host; without a CUDA device
+// every entry point fails (there is no CPU fallback by design).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "env_kernels.cuh"
+
+using namespace merlin;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t err, const char* what) {
+  return fail(MERLIN_ECUDA, std::string(what) + ": " + cudaGetErrorString(err));
+}
+
+struct DeviceGuard {  // the caller (e.g. torch) owns the current-device setting; restore it on exit
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+struct merlin_env {
+  merlin_env_config_t cfg{};
+  int sm_count = 0;
+  int cell_stride = 0;
+  int vis_words = 0;
+  int n_layouts = 0;
+  bool mutable_grid = false;
+  bool has_atlas = false;
+  bool was_reset = false;
+  int64_t launches = 0;
+  // device memory
+  int4* state = nullptr;
+  float* ep_return = nullptr;
+  uint8_t* cells = nullptr;
+  uint32_t* visited = nullptr;
+  uint8_t* pool_cells = nullptr;
+  uint32_t* pool_agent = nullptr;
+  uint8_t* atlas = nullptr;
+  unsigned long long* bad_actions = nullptr;
+};
+
+static EnvParams base_params(const merlin_env* h) {
+  EnvParams p{};
+  p.N = h->cfg.n_envs; p.W = h->cfg.width; p.H = h->cfg.height; p.max_steps = h->cfg.max_steps;
+  p.cell_stride = h->cell_stride; p.n_layouts = h->n_layouts; p.vis_words = h->vis_words;
+  p.stuck_max_stay = h->cfg.stuck_max_stay; p.flags = h->cfg.flags;
+  p.stuck_penalty = h->cfg.stuck_penalty; p.explore_bonus = h->cfg.explore_bonus;
+  p.state = h->state; p.ep_return = h->ep_return; p.cells = h->cells; p.visited = h->visited;
+  p.pool_cells = h->pool_cells; p.pool_agent = h->pool_agent; p.atlas = h->atlas; p.bad_actions = h->bad_actions;
+  return p;
+}
+
+extern "C" {
+
+void merlin_env_default_config(merlin_env_config_t* cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0; cfg->n_envs = 1; cfg->width = 16; cfg->height = 16; cfg->max_steps = 0;
+  cfg->view = kView; cfg->tile = kTile; cfg->flags = MERLIN_F_AUTO_RESET;
+  cfg->stuck_max_stay = 3; cfg->stuck_penalty = -0.1; cfg->explore_bonus = 0.0;
+}
+
+int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
+  if (!cfg || !out) return fail(MERLIN_EINVAL, "merlin_env_create: null argument");
+  *out = nullptr;
+  if (cfg->n_envs < 1) return fail(MERLIN_EINVAL, "n_envs must be >= 1");
+  if (cfg->width < 3 || cfg->width > 255 || cfg->height < 3 || cfg->height > 255)
+    return fail(MERLIN_EINVAL, "width/height must be in [3,255]");
+  if (cfg->view != kView) return fail(MERLIN_EINVAL, "only agent_view_size 7 is built");
+  if (cfg->tile != kTile) return fail(MERLIN_EINVAL, "only tile size 8 is built");
+  if (cfg->max_steps < 0) return fail(MERLIN_EINVAL, "max_steps must be >= 0");
+  if (cfg->stuck_max_stay < 0 || cfg->stuck_max_stay > 0xffff) return fail(MERLIN_EINVAL, "stuck_max_stay out of range");
+  int n_dev = 0;
+  cudaError_t err = cudaGetDeviceCount(&n_dev);
+  if (err != cudaSuccess || n_dev == 0)
+    return fail(MERLIN_ECUDA, "no CUDA device: libmerlin_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(MERLIN_EINVAL, "bad device ordinal");
+  DeviceGuard guard(cfg->device);
+  if (!guard.ok) return fail(MERLIN_ECUDA, "cudaSetDevice failed");
+
+  merlin_env* h = new (std::nothrow) merlin_env();
+  if (!h) return fail(MERLIN_ENOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  if (h->cfg.max_steps == 0) h->cfg.max_steps = 4 * cfg->width * cfg->height;  // base_env.py:32-33
+  h->cell_stride = (cfg->width * cfg->height + 15) & ~15;
+  h->mutable_grid = (cfg->flags & MERLIN_F_SEVEN_ACTIONS) != 0;  // only pickup/drop/toggle write the grid
+  h->vis_words = (cfg->width * cfg->height + 31) / 32;
+  cudaDeviceProp prop{};
+  if ((err = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) { delete h; return cuda_fail(err, "cudaGetDeviceProperties"); }
+  h->sm_count = prop.multiProcessorCount;
+
+  const size_t N = (size_t)cfg->n_envs;
+  bool ok = true;
+  ok = ok && cudaMalloc(&h->state, N * sizeof(int4)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->ep_return, N * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
+  if (ok && h->mutable_grid) ok = cudaMalloc(&h->cells, N * h->cell_stride) == cudaSuccess;
+  if (ok && (cfg->flags & MERLIN_F_EXPLORE_BONUS)) ok = cudaMalloc(&h->visited, N * h->vis_words * sizeof(uint32_t)) == cudaSuccess;
+  if (!ok) {
+    err = cudaGetLastError();
+    merlin_env_destroy(h);
+    return fail(MERLIN_ENOMEM, std::string("device allocation failed: ") + cudaGetErrorString(err));
+  }
+  cudaMemset(h->state, 0, N * sizeof(int4));
+  cudaMemset(h->ep_return, 0, N * sizeof(float));
+  cudaMemset(h->bad_actions, 0, sizeof(unsigned long long));
+  cudaMemset(h->atlas, 0, kAtlasBytes);
+  if (h->cells) cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride);
+  if (h->visited) cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t));
+  if ((err = cudaDeviceSynchronize()) != cudaSuccess) { merlin_env_destroy(h); return cuda_fail(err, "init"); }
+  *out = h;
+  return MERLIN_OK;
+}
+
+int merlin_env_destroy(merlin_env_t* h) {
+  if (!h) return MERLIN_OK;
+  DeviceGuard guard(h->cfg.device);
+  cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
+  cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
+  delete h;
+  return MERLIN_OK;
+}
+
+int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32_t* agent_xyd, int32_t n_layouts) {
+  if (!h || !cells || !agent_xyd || n_layouts < 1) return fail(MERLIN_EINVAL, "merlin_env_upload_layouts: bad argument");
+  const int W = h->cfg.width, H = h->cfg.height, HW = W * H;
+  std::vector<uint8_t> packed((size_t)n_layouts * h->cell_stride, (uint8_t)CODE_EMPTY);
+  std::vector<uint32_t> agent((size_t)n_layouts);
+  for (int l = 0; l < n_layouts; ++l) {
+    for (int k = 0; k < HW; ++k) {
+      const uint8_t c = cells[(size_t)l * HW + k];
+      const uint32_t t = c & 0xf, col = (c >> 4) & 7;
+      const bool type_ok = (t >= T_EMPTY && t <= T_LAVA) || t == T_DOOR_CLOSED || t == T_DOOR_LOCKED;
+      if (!type_ok || col > 5 || (c & 0x80)) {
+        char msg[128];
+        std::snprintf(msg, sizeof msg, "layout %d cell %d: invalid packed code 0x%02x", l, k, c);
+        return fail(MERLIN_EINVAL, msg);
+      }
+      packed[(size_t)l * h->cell_stride + k] = c;
+    }
+    const int x = agent_xyd[3 * l], y = agent_xyd[3 * l + 1], d = agent_xyd[3 * l + 2];
+    if (x < 0 || x >= W || y < 0 || y >= H || d < 0 || d > 3) return fail(MERLIN_EINVAL, "agent pose outside the grid");
+    const uint32_t under = packed[(size_t)l * h->cell_stride + y * W + x] & 0xf;
+    if (!((M_OVERLAP >> under) & 1u)) return fail(MERLIN_EINVAL, "agent placed on a non-overlappable cell");
+    agent[l] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)d << 16);
+  }
+  DeviceGuard guard(h->cfg.device);
+  uint8_t* d_cells = nullptr;
+  uint32_t* d_agent = nullptr;
+  if (cudaMalloc(&d_cells, packed.size()) != cudaSuccess || cudaMalloc(&d_agent, agent.size() * sizeof(uint32_t)) != cudaSuccess) {
+    cudaFree(d_cells);
+    return cuda_fail(cudaGetLastError(), "layout pool allocation");
+  }
+  cudaError_t err = cudaMemcpy(d_cells, packed.data(), packed.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(d_agent, agent.data(), agent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) { cudaFree(d_cells); cudaFree(d_agent); return cuda_fail(err, "layout upload"); }
+  cudaDeviceSynchronize();  // nothing may still be reading the old pool
+  cudaFree(h->pool_cells); cudaFree(h->pool_agent);
+  h->pool_cells = d_cells; h->pool_agent = d_agent; h->n_layouts = n_layouts;
+  h->was_reset = false;
+  return merlin_env_set_cursors(h, nullptr);
+}
+
+int merlin_env_set_tile_atlas(merlin_env_t* h, const uint8_t* tiles, int32_t n_tiles) {
+  if (!h || !tiles || n_tiles != kAtlasTiles) return fail(MERLIN_EINVAL, "atlas must hold exactly 128 tiles of 8x8x3");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaMemcpy(h->atlas, tiles, kAtlasBytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cuda_fail(err, "atlas upload");
+  h->has_atlas = true;
+  return MERLIN_OK;
+}
+
+int merlin_env_set_cursors(merlin_env_t* h, const int32_t* cursor) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (h->n_layouts < 1) return fail(MERLIN_ESTATE, "upload layouts first");
+  const int N = h->cfg.n_envs;
+  std::vector<int4> st((size_t)N);
+  for (int e = 0; e < N; ++e) {
+    const int c = cursor ? cursor[e] : e % h->n_layouts;
+    if (c < 0 || c >= h->n_layouts) return fail(MERLIN_EINVAL, "cursor outside the layout pool");
+    st[e] = make_int4(0, 0, ~c, 0);  // negative layout = pending first load
+  }
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaMemcpy(h->state, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cuda_fail(err, "cursor upload");
+  h->was_reset = false;
+  return MERLIN_OK;
+}
+
+int merlin_env_reset(merlin_env_t* h, const uint8_t* mask, uint8_t* obs_rgb, uint8_t* obs_sym, void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (h->n_layouts < 1) return fail(MERLIN_ESTATE, "reset before layouts were uploaded");
+  if (obs_rgb && !h->has_atlas) return fail(MERLIN_ESTATE, "RGB observation requested before the tile atlas was set");
+  if (mask && !h->was_reset) return fail(MERLIN_ESTATE, "the first reset must cover every env (mask = NULL)");
+  if (obs_rgb && (reinterpret_cast<uintptr_t>(obs_rgb) & 15)) return fail(MERLIN_EINVAL, "obs_rgb must be 16-byte aligned");
+  DeviceGuard guard(h->cfg.device);
+  EnvParams p = base_params(h);
+  p.reset_mask = mask; p.obs_rgb = obs_rgb; p.obs_sym = obs_sym;
+  cudaError_t err = launch_env_reset(p, h->sm_count, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "env reset launch");
+  h->launches += 1;
+  h->was_reset = true;
+  return MERLIN_OK;
+}
+
+int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
+                    uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (!actions || !reward || !terminated || !truncated) return fail(MERLIN_EINVAL, "actions/reward/terminated/truncated are required");
+  if (!h->was_reset) return fail(MERLIN_ESTATE, "step before reset");
+  if (obs_rgb && !h->has_atlas) return fail(MERLIN_ESTATE, "RGB observation requested before the tile atlas was set");
+  if (obs_rgb && (reinterpret_cast<uintptr_t>(obs_rgb) & 15)) return fail(MERLIN_EINVAL, "obs_rgb must be 16-byte aligned");
+  DeviceGuard guard(h->cfg.device);
+  EnvParams p = base_params(h);
+  p.actions = actions; p.obs_rgb = obs_rgb; p.obs_sym = obs_sym;
+  p.reward = reward; p.terminated = terminated; p.truncated = truncated;
+  if (extras) { p.out_ep_return = extras->episode_return; p.out_ep_length = extras->episode_length; p.out_stuck = extras->stuck; }
+  cudaError_t err = launch_env_step(p, h->sm_count, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "env step launch");
+  h->launches += 1;
+  return MERLIN_OK;
+}
+
+int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state, uint8_t** cells, int32_t* cell_stride, float** episode_return) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (state) *state = reinterpret_cast<int32_t*>(h->state);
+  if (cells) *cells = h->cells;
+  if (cell_stride) *cell_stride = h->cell_stride;
+  if (episode_return) *episode_return = h->ep_return;
+  return MERLIN_OK;
+}
+
+int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float* episode_return) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (cells && !h->cells) return fail(MERLIN_ESTATE, "grids are immutable: index the layout pool by state[e][2]");
+  DeviceGuard guard(h->cfg.device);
+  const size_t N = (size_t)h->cfg.n_envs;
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err == cudaSuccess && state) err = cudaMemcpy(state, h->state, N * sizeof(int4), cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && episode_return) err = cudaMemcpy(episode_return, h->ep_return, N * sizeof(float), cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && cells) {
+    const size_t HW = (size_t)h->cfg.width * h->cfg.height;
+    err = cudaMemcpy2D(cells, HW, h->cells, h->cell_stride, HW, N, cudaMemcpyDeviceToHost);
+  }
+  if (err != cudaSuccess) return cuda_fail(err, "state read-back");
+  return MERLIN_OK;
+}
+
+int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count) {
+  if (!h || !count) return fail(MERLIN_EINVAL, "null argument");
+  DeviceGuard guard(h->cfg.device);
+  unsigned long long v = 0;
+  cudaError_t err = cudaMemcpy(&v, h->bad_actions, sizeof v, cudaMemcpyDeviceToHost);
+  if (err != cudaSuccess) return cuda_fail(err, "bad-action counter read");
+  *count = v;
+  return MERLIN_OK;
+}
+
+int64_t merlin_env_launch_count(merlin_env_t* h) { return h ? h->launches : 0; }
+
+int merlin_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv, float* ret,
+               int32_t T, int32_t N, double gamma, double lam, void* stream) {
+  if (!rew || !val || !done || !last_val || !adv || !ret) return fail(MERLIN_EINVAL, "merlin_gae: null pointer");
+  if (T < 0 || N < 0) return fail(MERLIN_EINVAL, "merlin_gae: negative size");
+  if (T == 0 || N == 0) return MERLIN_OK;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(MERLIN_ECUDA, "no CUDA device: libmerlin_b200 has no CPU fallback");
+  cudaError_t err = launch_gae(rew, val, done, last_val, adv, ret, T, N, gamma, lam, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "gae launch");
+  return MERLIN_OK;
+}
+
+uint8_t merlin_pack_cell(int type, int color, int state) {
+  uint32_t t = (uint32_t)type & 0xf;
+  if (t == 0) t = T_EMPTY;
+  if (t == 4) t = state == 1 ? T_DOOR_CLOSED : (state == 2 ? T_DOOR_LOCKED : T_DOOR_OPEN);
+  uint32_t c = (uint32_t)color & 7;
+  if (t == T_GOAL) c = 1;                   // upstream Goal() is always green, Lava() red, None has no colour
+  if (t == T_LAVA || t == T_EMPTY) c = 0;
+  return (uint8_t)(t | (c << 4));
+}
+
+const char* merlin_last_error(void) { return g_last_error.c_str(); }
+const char* merlin_version(void) { return "merlin_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

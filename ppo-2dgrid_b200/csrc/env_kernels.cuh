@@ -1,0 +1,54 @@
+// env_kernels.cuh -- launch interface between the C ABI (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/merlin_b200.h"
+#include "env_logic.cuh"
+
+namespace merlin {
+
+constexpr int kThreads = 256;                 // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576
+constexpr int kKindStride = 52;               // 49 tile kinds per env, padded: odd word stride -> conflict-free lanes
+constexpr int kChunksPerLane = (kChunks + 31) / 32;     // 19
+
+__host__ __device__ constexpr int warp_smem_bytes(int G) {
+  return (G * kKindStride + G * kSymBytes + 15) & ~15;
+}
+__host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + kWarps * warp_smem_bytes(G); }
+
+struct EnvParams {
+  // geometry / behaviour
+  int N, W, H, max_steps, cell_stride, n_layouts, vis_words, stuck_max_stay;
+  uint32_t flags;
+  double stuck_penalty, explore_bonus;
+  // handle-owned device state
+  int4* state;                 // [N] pose | step_count | layout | stuck
+  float* ep_return;            // [N] running episode return
+  uint8_t* cells;              // [N][cell_stride] private grids, or nullptr when grids are immutable
+  uint32_t* visited;           // [N][vis_words] per-episode visited bitmap, or nullptr
+  const uint8_t* pool_cells;   // [L][cell_stride]
+  const uint32_t* pool_agent;  // [L] x | y<<8 | dir<<16
+  const uint8_t* atlas;        // [128][192]
+  unsigned long long* bad_actions;
+  // caller-owned I/O
+  const int64_t* actions;
+  const uint8_t* reset_mask;
+  uint8_t* obs_rgb;
+  uint8_t* obs_sym;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  float* out_ep_return;
+  int32_t* out_ep_length;
+  uint8_t* out_stuck;
+};
+
+cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
+                       float* ret, int T, int N, double gamma, double lam, cudaStream_t stream);
+
+}  // namespace merlin

@@ -1,0 +1,224 @@
+// env_logic.cuh -- per-environment arithmetic of the MERLIN rollout hot path, written once as
+// host+device inline functions.  The CUDA kernels in env_kernels.cu call these per lane; the
+// host-only model in tests/csrc/host_model.cpp compiles the SAME functions with g++ so the logic can
+// be checked against the oracle in the CPU test tier (it is a test vehicle, not a CPU fallback: the
+// product library exports no host compute path).
+//
+// What each function restates (reference anchors; upstream = minigrid 3.0.0, un-vendored):
+//   step_logic      MiniGridEnv.step  [upstream]           reached from src/ppo.py:76, src/fomaml.py:71
+//                   ThreeActionWrapper                      src/wrappers/three_action_wrapper.py:10-17
+//   shape_reward    StuckPenaltyWrapper.step                src/wrappers/stuck_penalty_wrapper.py:29-58
+//                   + first-visit exploration bonus (builder-specified; absent from the reference)
+//   gather_view     get_view_exts + Grid.slice + rotate_left x (dir+1) [upstream], as the closed form
+//                   world = agent + (6 - vj) * f + (vi - 3) * r        
+//   visibility      Grid.process_vis [upstream] as 7-bit row masks     
+//   cell_kind / sym_of_code   Grid.encode / Grid.render tile choice [upstream]
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MERLIN_HD __host__ __device__ __forceinline__
+#else
+#define MERLIN_HD inline
+#endif
+
+namespace merlin {
+
+constexpr int kView = 7;                              // agent_view_size (upstream default; base_env.py passes none)
+constexpr int kTile = 8;                              // RGBImgPartialObsWrapper tile_size default
+constexpr int kCells = kView * kView;                 // 49
+constexpr int kRowBytes = kView * kTile * 3;          // 168
+constexpr int kImgBytes = kRowBytes * kView * kTile;  // 9408
+constexpr int kChunks = kImgBytes / 16;               // 588 16-byte chunks per frame
+constexpr int kUnitsPerRow = kRowBytes / 8;           // 21 8-byte units per pixel row
+constexpr int kSymBytes = kCells * 3;                 // 147
+constexpr int kTileBytes = kTile * kTile * 3;         // 192
+constexpr int kAtlasTiles = 128;
+
+// packed cell codes (see include/merlin_b200.h)
+constexpr uint32_t T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR_OPEN = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7,
+                   T_GOAL = 8, T_LAVA = 9, T_AGENT = 10, T_DOOR_CLOSED = 11, T_DOOR_LOCKED = 12;
+constexpr uint32_t CODE_EMPTY = 1;
+constexpr uint32_t CODE_WALL = T_WALL | (5u << 4);  // grey wall: what Grid.slice puts outside the grid
+constexpr uint32_t KIND_UNSEEN = 0;                 // atlas slot of an invisible (erased, un-highlighted) cell
+constexpr uint32_t KIND_AGENT = T_AGENT;            // agent triangle over an empty highlighted cell
+
+// type-indexed predicate bitmasks
+constexpr uint32_t M_OVERLAP = (1u << T_EMPTY) | (1u << T_FLOOR) | (1u << T_DOOR_OPEN) | (1u << T_GOAL) | (1u << T_LAVA);
+constexpr uint32_t M_PICKUP = (1u << T_KEY) | (1u << T_BALL) | (1u << T_BOX);
+constexpr uint32_t M_OPAQUE = (1u << T_WALL) | (1u << T_DOOR_CLOSED) | (1u << T_DOOR_LOCKED);
+
+// actions (MiniGridEnv.Actions)
+enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
+
+struct EnvState {
+  int x, y, dir;        // agent pose
+  uint32_t carry;       // packed code of the carried object, 0 = nothing
+  int step_count;
+  int layout;           // pool index of the loaded layout; negative = ~index pending for the first reset
+  int stay;             // StuckPenalty counter
+  int last_x, last_y;   // StuckPenalty last position
+};
+
+MERLIN_HD void unpack_state(int sx, int sy, int sz, int sw, EnvState& s) {
+  s.x = sx & 0xff; s.y = (sx >> 8) & 0xff; s.dir = (sx >> 16) & 3; s.carry = ((uint32_t)sx >> 24) & 0x7f;
+  s.step_count = sy; s.layout = sz;
+  s.stay = sw & 0xffff; s.last_x = (sw >> 16) & 0xff; s.last_y = ((uint32_t)sw >> 24) & 0xff;
+}
+MERLIN_HD void pack_state(const EnvState& s, int& sx, int& sy, int& sz, int& sw) {
+  sx = s.x | (s.y << 8) | (s.dir << 16) | (int)(s.carry << 24);
+  sy = s.step_count; sz = s.layout;
+  int stay = s.stay > 0xffff ? 0xffff : s.stay;
+  sw = stay | (s.last_x << 16) | (int)((uint32_t)s.last_y << 24);
+}
+
+MERLIN_HD int dir_dx(int d) { return d == 0 ? 1 : (d == 2 ? -1 : 0); }
+MERLIN_HD int dir_dy(int d) { return d == 1 ? 1 : (d == 3 ? -1 : 0); }
+
+struct StepResult {
+  double reward;
+  bool terminated, truncated, bad_action;
+  int write_idx;        // >= 0: grid cell index to overwrite with write_code (pickup/drop/toggle)
+  uint32_t write_code;
+};
+
+// MiniGridEnv.step on one env. `fwd` is the packed code in front of the agent (CODE_WALL when outside the grid).
+MERLIN_HD StepResult step_logic(EnvState& s, long long action, int n_actions, uint32_t fwd, bool fwd_in_grid,
+                                int fwd_idx, int max_steps) {
+  StepResult r;
+  r.reward = 0.0; r.terminated = false; r.truncated = false; r.write_idx = -1; r.write_code = 0;
+  r.bad_action = (action < 0 || action >= n_actions);
+  const int a = r.bad_action ? A_DONE : (int)action;  // 3-action mode: {0,1,2} are already left/right/forward
+  s.step_count += 1;
+  const uint32_t ft = fwd & 0xf;
+  const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
+  if (a == A_LEFT) {
+    s.dir = (s.dir + 3) & 3;
+  } else if (a == A_RIGHT) {
+    s.dir = (s.dir + 1) & 3;
+  } else if (a == A_FORWARD) {
+    if ((M_OVERLAP >> ft) & 1u) { s.x = fx; s.y = fy; }
+    if (ft == T_GOAL) {
+      r.terminated = true;
+      r.reward = 1 - 0.9 * ((double)s.step_count / (double)max_steps);  // MiniGridEnv._reward, float64
+    }
+    if (ft == T_LAVA) r.terminated = true;
+  } else if (a == A_PICKUP) {
+    if (((M_PICKUP >> ft) & 1u) && s.carry == 0 && fwd_in_grid) {
+      s.carry = fwd; r.write_idx = fwd_idx; r.write_code = CODE_EMPTY;
+    }
+  } else if (a == A_DROP) {
+    if (ft == T_EMPTY && s.carry != 0 && fwd_in_grid) {
+      r.write_idx = fwd_idx; r.write_code = s.carry; s.carry = 0;
+    }
+  } else if (a == A_TOGGLE) {
+    if (fwd_in_grid) {
+      const uint32_t col = fwd & 0x70;
+      if (ft == T_DOOR_LOCKED) {
+        if ((s.carry & 0xf) == T_KEY && (s.carry & 0x70) == col) { r.write_idx = fwd_idx; r.write_code = col | T_DOOR_OPEN; }
+      } else if (ft == T_DOOR_CLOSED) {
+        r.write_idx = fwd_idx; r.write_code = col | T_DOOR_OPEN;
+      } else if (ft == T_DOOR_OPEN) {
+        r.write_idx = fwd_idx; r.write_code = col | T_DOOR_CLOSED;
+      } else if (ft == T_BOX) {
+        r.write_idx = fwd_idx; r.write_code = CODE_EMPTY;  // boxes are empty here: replaced by their (None) contents
+      }
+    }
+  }
+  if (s.step_count >= max_steps) r.truncated = true;
+  return r;
+}
+
+// Wrapper-stack reward shaping, in float64 like the python floats of the reference, cast to f32 by the caller.
+// visited_word: the 32-bit word of the per-episode visited bitmap holding the agent's cell (in/out).
+MERLIN_HD double shape_reward(EnvState& s, double reward, bool stuck_on, int max_stay, double penalty, bool explore_on,
+                              double bonus, uint32_t& visited_word, int cell_bit, bool& stuck) {
+  stuck = false;
+  if (stuck_on) {
+    s.stay = (s.x == s.last_x && s.y == s.last_y) ? s.stay + 1 : 0;
+    if (s.stay >= max_stay) { reward += penalty; stuck = true; }
+    s.last_x = s.x; s.last_y = s.y;
+  }
+  if (explore_on) {
+    const uint32_t bit = 1u << cell_bit;
+    if (!(visited_word & bit)) { visited_word |= bit; reward += bonus; }
+  }
+  return reward;
+}
+
+// Egocentric 7x7 window. kind[vi*7+vj] receives the packed code (CODE_WALL outside the grid); returns the
+// 49-bit transparency mask, bit (vj*7 + vi).  `cells` is the env's row-major grid.
+template <typename LoadCell>
+MERLIN_HD uint64_t gather_view(const EnvState& s, int W, int H, LoadCell load, uint8_t* kind) {
+  const int fx = dir_dx(s.dir), fy = dir_dy(s.dir);
+  const int rx = -fy, ry = fx;
+  uint64_t transp = 0;
+#pragma unroll
+  for (int vj = 0; vj < kView; ++vj) {
+#pragma unroll
+    for (int vi = 0; vi < kView; ++vi) {
+      const int a = (kView - 1) - vj, b = vi - kView / 2;
+      const int wx = s.x + a * fx + b * rx;
+      const int wy = s.y + a * fy + b * ry;
+      uint32_t code = CODE_WALL;
+      if ((unsigned)wx < (unsigned)W && (unsigned)wy < (unsigned)H) code = load(wy * W + wx);
+      kind[vi * kView + vj] = (uint8_t)code;
+      if (!((M_OPAQUE >> (code & 0xf)) & 1u)) transp |= (uint64_t)1 << (vj * kView + vi);
+    }
+  }
+  return transp;
+}
+
+// Grid.process_vis(agent_pos=(3,6)) on row bitmasks; returns the 49-bit visibility mask, bit (vj*7 + vi).
+MERLIN_HD uint64_t visibility(uint64_t transp) {
+  uint64_t vis = 0;
+  uint32_t seed = 1u << (kView / 2);
+#pragma unroll
+  for (int vj = kView - 1; vj >= 0; --vj) {
+    const uint32_t T = (uint32_t)(transp >> (vj * kView)) & 0x7f;
+    uint32_t v = seed;
+    const uint32_t TL = T & 0x3f;  // cells 0..5 may push right
+#pragma unroll
+    for (int k = 0; k < kView - 1; ++k) v |= (v & TL) << 1;
+    const uint32_t A = v & TL;
+    const uint32_t TR = T & 0x7e;  // cells 6..1 may push left
+#pragma unroll
+    for (int k = 0; k < kView - 1; ++k) v |= (v & TR) >> 1;
+    const uint32_t B = v & TR;
+    vis |= (uint64_t)v << (vj * kView);
+    seed = (A | (A << 1) | B | (B >> 1)) & 0x7f;
+  }
+  return vis;
+}
+
+// Atlas slot shown for the agent cell (view (3,6)): the carried object under the agent triangle.
+MERLIN_HD uint32_t agent_kind(uint32_t carry) {
+  return carry == 0 ? KIND_AGENT : ((carry & 0x70) | ((carry & 0xf) + 8));  // key/ball/box -> 13/14/15
+}
+
+// (type, colour, state) bytes of Grid.encode for a packed code.
+MERLIN_HD void sym_of_code(uint32_t code, uint8_t& t, uint8_t& c, uint8_t& st) {
+  const uint32_t ty = code & 0xf;
+  c = (uint8_t)((code >> 4) & 7);
+  if (ty == T_DOOR_CLOSED) { t = 4; st = 1; }
+  else if (ty == T_DOOR_LOCKED) { t = 4; st = 2; }
+  else { t = (uint8_t)ty; st = 0; }
+}
+
+// Chunk lookup for the RGB blit: 16-byte chunk c of the 56x56x3 frame is two 8-byte units; each unit lies in
+// one tile row.  Returns cell0 | off0<<8 | cell1<<16 | off1<<24 with cell = vi*7+vj and off = py*3 + part
+// (the 8-byte unit index inside the 192-byte tile).
+MERLIN_HD uint32_t chunk_lut(int c) {
+  uint32_t packed = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int u = 2 * c + h;
+    const int row = u / kUnitsPerRow, w = u - row * kUnitsPerRow;
+    const int vi = w / 3, part = w - vi * 3;
+    const int vj = row / kTile, py = row - vj * kTile;
+    packed |= (uint32_t)((vi * kView + vj) | ((py * 3 + part) << 8)) << (16 * h);
+  }
+  return packed;
+}
+
+}  // namespace merlin

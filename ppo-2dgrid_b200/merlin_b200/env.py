@@ -1,0 +1,188 @@
+"""BatchedMerlinEnv -- N MiniGrid/MERLIN environments stepped by one fused CUDA kernel per call.
+
+Host-side mirror of the reference env interface for the batched case: `reset()` / `step(actions)` with the
+gymnasium 5-tuple, observations as the policy consumes them (`u8[N, 56, 56, 3]`, the
+RGBImgPartialObsWrapper + ImgObsWrapper output of src/scenario_creator/scenario_creator.py:45-50), the
+ThreeActionWrapper action set (src/wrappers/three_action_wrapper.py) and optional StuckPenaltyWrapper
+semantics (src/wrappers/stuck_penalty_wrapper.py).  Everything stays on the device; this class only owns
+tensors and forwards pointers through the C ABI (include/merlin_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, codes, tiles
+
+VIEW, TILE = 7, 8
+OBS_SHAPE = (VIEW * TILE, VIEW * TILE, 3)
+SYM_SHAPE = (VIEW, VIEW, 3)
+
+
+class BatchedMerlinEnv:
+    def __init__(self, num_envs, cells=None, agent=None, *, enc=None, width=None, height=None, max_steps=None,
+                 device="cuda", n_actions=3, auto_reset=True, reset_mode="next", stuck_penalty=False,
+                 stuck_max_stay=3, stuck_penalty_value=-0.1, exploration_bonus=0.0, want_symbolic=True,
+                 want_rgb=True):
+        """cells: packed u8[L, H*W] (merlin_b200.codes) or `enc`: Grid.encode() arrays u8[L, W, H, 3];
+        agent: i32[L, 3] = (x, y, dir).  `reset_mode`: "next" advances each env's pool cursor by num_envs at
+        every restart (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedMerlinEnv needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if reset_mode not in ("next", "same"):
+            raise ValueError("reset_mode must be 'next' or 'same'")
+        if n_actions not in (3, 7):
+            raise ValueError("n_actions must be 3 (ThreeActionWrapper) or 7 (full MiniGrid set)")
+        if enc is not None:
+            enc = np.asarray(enc)
+            width, height = enc.shape[1], enc.shape[2]
+            cells = codes.pack_encoding(enc)
+        if cells is None or agent is None:
+            raise ValueError("a layout pool (cells or enc, and agent) is required")
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        if width is None:
+            width = height = int(round(cells.shape[1] ** 0.5))
+        self.num_envs, self.width, self.height = int(num_envs), int(width), int(height)
+        self.n_actions = n_actions
+        self.want_symbolic, self.want_rgb = want_symbolic, want_rgb
+        self.auto_reset = auto_reset
+
+        self._lib = _lib.load()
+        cfg = _lib.EnvConfig()
+        self._lib.merlin_env_default_config(C.byref(cfg))
+        cfg.device = self.device.index
+        cfg.n_envs, cfg.width, cfg.height = self.num_envs, self.width, self.height
+        cfg.max_steps = int(max_steps) if max_steps else 0
+        flags = 0
+        flags |= _lib.F_AUTO_RESET if auto_reset else 0
+        flags |= _lib.F_RESET_SAME if reset_mode == "same" else 0
+        flags |= _lib.F_SEVEN_ACTIONS if n_actions == 7 else 0
+        flags |= _lib.F_STUCK_PENALTY if stuck_penalty else 0
+        flags |= _lib.F_EXPLORE_BONUS if exploration_bonus != 0.0 else 0
+        cfg.flags = flags
+        cfg.stuck_max_stay, cfg.stuck_penalty = int(stuck_max_stay), float(stuck_penalty_value)
+        cfg.explore_bonus = float(exploration_bonus)
+        self.max_steps = cfg.max_steps or 4 * self.width * self.height
+        self._h = C.c_void_p()
+        _lib.check(self._lib.merlin_env_create(C.byref(cfg), C.byref(self._h)))
+        if want_rgb:
+            atlas = np.ascontiguousarray(tiles.build_atlas(TILE))
+            _lib.check(self._lib.merlin_env_set_tile_atlas(self._h, atlas.ctypes.data, atlas.shape[0]))
+        self.upload_layouts(cells, agent)
+
+        N, dev = self.num_envs, self.device
+        self.obs = torch.empty((N,) + OBS_SHAPE, dtype=torch.uint8, device=dev) if want_rgb else None
+        self.obs_symbolic = torch.empty((N,) + SYM_SHAPE, dtype=torch.uint8, device=dev) if want_symbolic else None
+        self.reward = torch.empty(N, dtype=torch.float32, device=dev)
+        self.terminated = torch.empty(N, dtype=torch.bool, device=dev)
+        self.truncated = torch.empty(N, dtype=torch.bool, device=dev)
+        self.episode_return = torch.empty(N, dtype=torch.float32, device=dev)
+        self.episode_length = torch.empty(N, dtype=torch.int32, device=dev)
+        self.stuck = torch.empty(N, dtype=torch.bool, device=dev)
+        self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
+                                       self.stuck.data_ptr())
+
+    # ---- pool ------------------------------------------------------------------------------------
+    def upload_layouts(self, cells, agent):
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        agent = np.ascontiguousarray(agent, dtype=np.int32).reshape(-1, 3)
+        if cells.ndim != 2 or cells.shape[1] != self.width * self.height or cells.shape[0] != agent.shape[0]:
+            raise ValueError(f"layout pool shape {cells.shape} does not match {self.width}x{self.height} / agent {agent.shape}")
+        _lib.check(self._lib.merlin_env_upload_layouts(self._h, cells.ctypes.data, agent.ctypes.data, cells.shape[0]))
+        self.n_layouts = cells.shape[0]
+        self._pool_cells_host = cells
+
+    def set_cursors(self, cursor=None):
+        """cursor[e] = pool index env e loads at its next (full) reset; None = e % n_layouts."""
+        if cursor is None:
+            _lib.check(self._lib.merlin_env_set_cursors(self._h, None))
+        else:
+            cur = np.ascontiguousarray(cursor, dtype=np.int32)
+            if cur.shape != (self.num_envs,):
+                raise ValueError("cursor must have one entry per env")
+            _lib.check(self._lib.merlin_env_set_cursors(self._h, cur.ctypes.data))
+
+    # ---- stepping --------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask=None, out_obs=None, out_symbolic=None):
+        """(Re)start all envs (mask=None) or those with mask[e] != 0.  Returns (obs_rgb, obs_symbolic)."""
+        obs = out_obs if out_obs is not None else self.obs
+        sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        _lib.check(self._lib.merlin_env_reset(self._h, mptr, obs.data_ptr() if obs is not None else None,
+                                              sym.data_ptr() if sym is not None else None, self._stream()))
+        return obs, sym
+
+    def step(self, actions, out_obs=None, out_symbolic=None):
+        """actions: int64 CUDA tensor [N] (numpy/int lists are copied over).  Returns the gymnasium 5-tuple
+        (obs u8[N,56,56,3], reward f32[N], terminated bool[N], truncated bool[N], info) with device tensors that
+        are REUSED by the next call unless `out_obs` / `out_symbolic` point into caller storage (e.g. a rollout slot)."""
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+        if actions.device != self.device or actions.dtype != torch.int64 or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int64).contiguous()
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        obs = out_obs if out_obs is not None else self.obs
+        sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
+        _lib.check(self._lib.merlin_env_step(
+            self._h, actions.data_ptr(), obs.data_ptr() if obs is not None else None,
+            sym.data_ptr() if sym is not None else None, self.reward.data_ptr(), self.terminated.data_ptr(),
+            self.truncated.data_ptr(), C.byref(self._extras), self._stream()))
+        info = {"episode_return": self.episode_return, "episode_length": self.episode_length, "stuck": self.stuck,
+                "obs_symbolic": sym}
+        return obs, self.reward, self.terminated, self.truncated, info
+
+    # ---- state views (synchronous host copies; debugging / tests / gym adapter) ------------------
+    def state_numpy(self):
+        """Host copy of the packed per-env state: dict of x, y, dir, carry, step_count, layout, stay, episode_return."""
+        a = np.empty((self.num_envs, 4), dtype=np.int32)
+        epr = np.empty(self.num_envs, dtype=np.float32)
+        _lib.check(self._lib.merlin_env_read_state(self._h, a.ctypes.data, None, epr.ctypes.data))
+        pose = a[:, 0].astype(np.int64) & 0xFFFFFFFF
+        stuck = a[:, 3].astype(np.int64) & 0xFFFFFFFF
+        return {"x": (pose & 0xFF).astype(np.int32), "y": ((pose >> 8) & 0xFF).astype(np.int32),
+                "dir": ((pose >> 16) & 3).astype(np.int32), "carry": ((pose >> 24) & 0x7F).astype(np.int32),
+                "step_count": a[:, 1].copy(), "layout": a[:, 2].copy(), "stay": (stuck & 0xFFFF).astype(np.int32),
+                "episode_return": epr}
+
+    def pose_numpy(self):
+        s = self.state_numpy()
+        return np.stack([s["x"], s["y"], s["dir"], s["step_count"]], axis=1)
+
+    def cells_numpy(self):
+        """Host copy of every env's current grid as packed cells [N, H*W]."""
+        if self.n_actions == 3:  # immutable grids: envs read the pool in place
+            return self._pool_cells_host[self.state_numpy()["layout"]]
+        out = np.empty((self.num_envs, self.width * self.height), dtype=np.uint8)
+        _lib.check(self._lib.merlin_env_read_state(self._h, None, out.ctypes.data, None))
+        return out
+
+    def bad_actions(self):
+        n = C.c_uint64()
+        _lib.check(self._lib.merlin_env_bad_actions(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count(self):
+        return int(self._lib.merlin_env_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.merlin_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

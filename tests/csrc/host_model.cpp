@@ -1,0 +1,71 @@
+// TEST VEHICLE (tests/ only) -- compiles the product's per-environment logic header
+// (ppo-2dgrid_b200/csrc/env_logic.cuh) for the HOST so the CPU test tier can check the exact functions the
+// CUDA kernels call (step_logic, shape_reward, gather_view, visibility, agent_kind, sym_of_code, chunk_lut)
+// against the oracle without a GPU.  It is not part of the product and is not shipped or loaded by it.
+#include <stdint.h>
+#include <string.h>
+
+#include "env_logic.cuh"
+
+using namespace merlin;
+
+extern "C" {
+
+// One step (no auto-reset) + observation for N envs. state: int32[N][4] packed like the device state.
+// cells: u8[N][cell_stride] private grids (mutated by pickup/drop/toggle). visited: u32[N][vis_words] or NULL.
+int hm_step(int N, int W, int H, int max_steps, int cell_stride, int n_actions, int do_step, int stuck_on,
+            int max_stay, double penalty, int explore_on, double bonus, int vis_words, int32_t* state, uint8_t* cells,
+            uint32_t* visited, const int64_t* actions, const uint8_t* atlas, uint8_t* obs_rgb, uint8_t* obs_sym,
+            float* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* stuck_out) {
+  for (int e = 0; e < N; ++e) {
+    EnvState s{};
+    int32_t* st = state + 4 * e;
+    unpack_state(st[0], st[1], st[2], st[3], s);
+    uint8_t* grid = cells + (size_t)e * cell_stride;
+    if (do_step) {
+      const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
+      const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+      const int fidx = fy * W + fx;
+      const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
+      StepResult r = step_logic(s, actions[e], n_actions, fwd, inb, fidx, max_steps);
+      if (r.write_idx >= 0) grid[r.write_idx] = (uint8_t)r.write_code;
+      uint32_t vword = 0;
+      const int cell = s.y * W + s.x;
+      if (explore_on) vword = visited[(size_t)e * vis_words + (cell >> 5)];
+      bool stuck = false;
+      const double rd = shape_reward(s, r.reward, stuck_on, max_stay, penalty, explore_on, bonus, vword, cell & 31, stuck);
+      if (explore_on) visited[(size_t)e * vis_words + (cell >> 5)] = vword;
+      reward[e] = (float)rd;
+      terminated[e] = r.terminated;
+      truncated[e] = r.truncated;
+      stuck_out[e] = stuck;
+      pack_state(s, st[0], st[1], st[2], st[3]);
+    }
+    uint8_t kind[kCells];
+    const uint64_t transp = gather_view(s, W, H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
+    const uint64_t vis = visibility(transp);
+    for (int vi = 0; vi < kView; ++vi)
+      for (int vj = 0; vj < kView; ++vj) {
+        const int c = vi * kView + vj;
+        const bool seen = (vis >> (vj * kView + vi)) & 1;
+        uint32_t code = kind[c];
+        const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
+        if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
+        kind[c] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
+        uint8_t t = 0, col = 0, stt = 0;
+        if (seen) sym_of_code(code, t, col, stt);
+        uint8_t* sym = obs_sym + (size_t)e * kSymBytes + c * 3;
+        sym[0] = t; sym[1] = col; sym[2] = stt;
+      }
+    uint8_t* frame = obs_rgb + (size_t)e * kImgBytes;
+    for (int c = 0; c < kChunks; ++c) {
+      const uint32_t q = chunk_lut(c);
+      const uint32_t k0 = kind[q & 0xff], k1 = kind[(q >> 16) & 0xff];
+      memcpy(frame + c * 16, atlas + k0 * kTileBytes + ((q >> 8) & 0xff) * 8, 8);
+      memcpy(frame + c * 16 + 8, atlas + k1 * kTileBytes + (q >> 24) * 8, 8);
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+"""CPU tests of the PRODUCT's host-side logic (no GPU):
+  * merlin_b200.layouts vs the fixtures made by the reference's own _gen_grid (same seeds -> same layouts)
+  * merlin_b200.tiles (array renderer) vs the literal per-pixel renderer of the oracle
+  * merlin_b200.codes round trips
+  * ppo-2dgrid_b200/csrc/env_logic.cuh -- the per-env functions the CUDA kernels call -- compiled for the host
+    (tests/csrc/host_model.cpp) and compared with the oracle on random grids, incl. doors/keys/boxes/lava.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from merlin_b200 import codes, layouts, tiles
+from oracle import fast
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+# ---- layouts ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", helpers.layout_names())
+def test_product_layouts_match_reference_fixtures(name):
+    fx = helpers.load(name + ".npz")
+    _, diff, size = name.split("_")
+    cells, agent = layouts.generate(diff, int(size), fx["seeds"])
+    assert np.array_equal(cells, codes.pack_encoding(fx["enc"]))
+    assert np.array_equal(agent, fx["agent"])
+
+
+@pytest.mark.parametrize("name", ["mediumhard_goal", "hard_goal", "hardest_goal", "medium_goal"])
+def test_product_layout_stream_matches_unseeded_resets(name):
+    tr = helpers.load(f"trace_{name}.npz")
+    n = tr["ep_enc"].shape[0]
+    cells, agent = layouts.generate_stream(str(tr["difficulty"]), int(tr["size"]), int(tr["seed"]), n)
+    assert np.array_equal(cells, codes.pack_encoding(tr["ep_enc"]))
+    assert np.array_equal(agent, tr["ep_agent"])
+
+
+def test_unknown_difficulty_raises_value_error():
+    with pytest.raises(ValueError):
+        layouts.generate("impossible", 16, [0])
+
+
+# ---- codes / tiles ------------------------------------------------------------------------------
+def test_codes_round_trip():
+    fx = helpers.load("layouts_hardest_16.npz")
+    packed = codes.pack_encoding(fx["enc"])
+    assert np.array_equal(codes.unpack_to_encoding(packed, 16, 16), fx["enc"])
+    assert codes.pack(4, 3, 1) == (codes.DOOR_CLOSED | (3 << 4)) and codes.pack(4, 3, 2) == (codes.DOOR_LOCKED | (3 << 4))
+    assert codes.pack(8, 5, 0) == codes.CODE_GOAL and codes.pack(0, 0, 0) == codes.CODE_EMPTY
+
+
+def test_atlas_matches_literal_renderer():
+    at = tiles.build_atlas()
+    oa = fast.TileAtlas(8)
+    assert np.array_equal(at[0], oa.tiles[fast.tile_slot(1, 0, 0, 0, 0)])
+    assert np.array_equal(at[1], oa.tiles[fast.tile_slot(1, 0, 0, 0, 1)])
+    assert np.array_equal(at[10], oa.tiles[fast.tile_slot(1, 0, 0, 1, 1)])
+    for color in range(6):
+        for t in codes.VALID_TYPES:
+            if t == codes.EMPTY:
+                continue
+            mt, st = (4, {4: 0, 11: 1, 12: 2}[t]) if t in (4, 11, 12) else (t, 0)
+            oa.ensure([(mt, color, st)])
+            assert np.array_equal(at[t | (color << 4)], oa.tiles[fast.tile_slot(mt, color, st, 0, 1)]), (t, color)
+            if t in (codes.KEY, codes.BALL, codes.BOX):
+                assert np.array_equal(at[(t + 8) | (color << 4)], oa.tiles[fast.tile_slot(mt, color, st, 1, 1)])
+
+
+# ---- env_logic.cuh on the host ----------------------------------------------------------------
+def _host_model():
+    src = os.path.join(ROOT, "tests", "csrc", "host_model.cpp")
+    hdr = os.path.join(ROOT, "ppo-2dgrid_b200", "csrc", "env_logic.cuh")
+    out = os.path.join(ROOT, "tests", "csrc", "_build", "libhost_model.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-I" + os.path.dirname(hdr), src, "-o", out])
+    lib = ctypes.CDLL(out)
+    lib.hm_step.restype = ctypes.c_int
+    return lib
+
+
+class HostModelEnv:
+    """The kernel's per-env logic driven from numpy (auto-reset off), for comparison with OracleVecEnv."""
+
+    def __init__(self, cells, agent, W, H, max_steps, n_actions=3, stuck=False, bonus=0.0):
+        self.lib = _host_model()
+        self.N, self.W, self.H, self.max_steps, self.n_actions = cells.shape[0], W, H, max_steps, n_actions
+        self.stride = (W * H + 15) & ~15
+        self.cells = np.full((self.N, self.stride), codes.CODE_EMPTY, np.uint8)
+        self.cells[:, : W * H] = cells
+        self.state = np.zeros((self.N, 4), np.int32)
+        self.state[:, 0] = agent[:, 0] | (agent[:, 1] << 8) | (agent[:, 2] << 16)
+        self.state[:, 3] = (agent[:, 0] << 16) | (agent[:, 1] << 24)
+        self.stuck_on, self.bonus = stuck, bonus
+        self.vw = (W * H + 31) // 32
+        self.visited = np.zeros((self.N, self.vw), np.uint32)
+        cell = agent[:, 1] * W + agent[:, 0]
+        self.visited[np.arange(self.N), cell >> 5] = (1 << (cell & 31)).astype(np.uint32)
+        self.atlas = np.ascontiguousarray(tiles.build_atlas())
+
+    def call(self, actions, do_step):
+        N = self.N
+        rgb = np.zeros((N, 56, 56, 3), np.uint8)
+        sym = np.zeros((N, 7, 7, 3), np.uint8)
+        rew = np.zeros(N, np.float32)
+        te, tr, sk = np.zeros(N, np.uint8), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        actions = np.ascontiguousarray(actions, np.int64)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.hm_step(N, self.W, self.H, self.max_steps, self.stride, self.n_actions, int(do_step), int(self.stuck_on),
+                         3, ctypes.c_double(-0.1), int(self.bonus != 0), ctypes.c_double(self.bonus), self.vw,
+                         p(self.state), p(self.cells), p(self.visited), p(actions), p(self.atlas), p(rgb), p(sym),
+                         p(rew), p(te), p(tr), p(sk))
+        return rgb, sym, rew, te.astype(bool), tr.astype(bool), sk.astype(bool)
+
+
+def _random_object_layouts(rng, L, size):
+    enc = np.zeros((L, size, size, 3), np.uint8)
+    enc[..., 0] = 1
+    enc[:, 0, :, :] = enc[:, -1, :, :] = enc[:, :, 0, :] = enc[:, :, -1, :] = (2, 5, 0)
+    agent = np.zeros((L, 3), np.int32)
+    objs = [(2, 5, 0), (2, 5, 0), (2, 5, 0), (8, 1, 0), (9, 0, 0), (3, 2, 0), (4, 4, 0), (4, 4, 1), (4, 4, 2),
+            (5, 4, 0), (6, 0, 0), (7, 3, 0), (4, 2, 1), (5, 2, 0)]
+    for l in range(L):
+        for _ in range(int(rng.integers(5, 30))):
+            x, y = rng.integers(1, size - 1, 2)
+            enc[l, x, y] = objs[int(rng.integers(0, len(objs)))]
+        while True:
+            x, y = rng.integers(1, size - 1, 2)
+            if enc[l, x, y, 0] == 1:
+                break
+        agent[l] = (x, y, rng.integers(0, 4))
+    return enc, agent
+
+
+@pytest.mark.parametrize("n_actions,stuck,bonus,size", [(3, False, 0.0, 16), (7, True, 0.0, 9), (7, False, 0.05, 12),
+                                                       (3, True, 0.01, 16)])
+def test_kernel_logic_on_host_matches_oracle(n_actions, stuck, bonus, size):
+    rng = np.random.default_rng(n_actions * 100 + size)
+    L = 64
+    if n_actions == 3:
+        cells, agent = layouts.generate("mediumhard", size, range(1000, 1000 + L))
+        enc = codes.unpack_to_encoding(cells, size, size)
+    else:
+        enc, agent = _random_object_layouts(rng, L, size)
+        cells = codes.pack_encoding(enc)
+    max_steps = 50
+    ref = fast.OracleVecEnv(L, enc, agent, max_steps=max_steps, n_actions=n_actions, auto_reset=False,
+                            stuck_penalty=stuck, exploration_bonus=bonus)
+    hm = HostModelEnv(cells, agent, size, size, max_steps, n_actions, stuck, bonus)
+    rgb0, sym0 = ref.reset()
+    rgb, sym, *_ = hm.call(np.zeros(L, np.int64), do_step=False)
+    assert np.array_equal(sym, sym0) and np.array_equal(rgb, rgb0)
+    for t in range(80):
+        a = rng.integers(0, n_actions, L)
+        if n_actions == 7:  # bias towards moving so objects get reached
+            a = np.where(rng.random(L) < 0.4, 2, a)
+        rgb0, r0, te0, tr0, info = ref.step(a)
+        rgb, sym, r, te, tr, sk = hm.call(a, do_step=True)
+        assert np.array_equal(r, r0), t
+        assert np.array_equal(te, te0) and np.array_equal(tr, tr0), t
+        assert np.array_equal(sk, info["stuck"]), t
+        assert np.array_equal(sym, info["obs_symbolic"]), t
+        assert np.array_equal(rgb, rgb0), t
+        pose = hm.state[:, 0]
+        assert np.array_equal(pose & 0xFF, ref.ax) and np.array_equal((pose >> 8) & 0xFF, ref.ay)
+        assert np.array_equal((pose >> 16) & 3, ref.adir) and np.array_equal(hm.state[:, 1], ref.stepc)
+
+
+def test_visibility_bitmask_exhaustive_rows():
+    """Bitmask process_vis vs the literal sweeps on 20k random 7x7 transparency patterns (via full envs)."""
+    rng = np.random.default_rng(99)
+    L, size = 512, 9
+    enc = np.zeros((L, size, size, 3), np.uint8)
+    enc[..., 0] = 1
+    walls = rng.random((L, size, size)) < rng.uniform(0.1, 0.6, (L, 1, 1))
+    enc[walls] = (2, 5, 0)
+    enc[:, 4, 4] = (1, 0, 0)
+    agent = np.tile(np.array([[4, 4, 0]], np.int32), (L, 1))
+    agent[:, 2] = rng.integers(0, 4, L)
+    ref = fast.OracleVecEnv(L, enc, agent, auto_reset=False)
+    hm = HostModelEnv(codes.pack_encoding(enc), agent, size, size, 100)
+    ref.reset()
+    for _ in range(40):
+        a = rng.integers(0, 2, L)  # spin in place: new headings over the same random walls
+        rgb0, _, _, _, info = ref.step(a)
+        rgb, sym, *_ = hm.call(a, do_step=True)
+        assert np.array_equal(sym, info["obs_symbolic"])
+        assert np.array_equal(rgb, rgb0)
