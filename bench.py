@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- batched env-steps/s of the fused MERLIN step kernel (step + gen_obs/process_vis + RGB render).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch: every env of the batch takes one action and gets its
+56x56x3 observation, reward and flags (BASELINE.json configs[1]: mediumhard 16x16, random actions, synthetic
+seeded layouts).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+  value      env-steps/s over all GPUs, inputs (actions) already in HBM, device-timed with CUDA events
+  e2e        same metric through the public host API with HOST action buffers: per step a pinned H2D copy of the
+             actions and a D2H read of reward/terminated/truncated; observations stay in HBM where the policy
+             consumes them (e2e.value_obs_to_host additionally copies every observation to the host: PCIe-bound)
+  roofline   algorithmic bytes per launch (9710 B x envs) / mean kernel time, against the measured HBM copy peak
+  cpu_baseline  the reference-style CPU path (oracle port: literal minigrid-3.0.0 restatement + wrapper stack),
+             one env per host core, bounded sample; plus the optimised C oracle as a second data point
+  --impl reference : only the CPU path, same metric/config, all host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "ppo-2dgrid_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "batched env-steps/sec (mediumhard 16x16, step+gen_obs+RGB render)"
+UNIT = "env-steps/s"
+SIZE = 16
+ALGO_BYTES_PER_STEP = 56 * 56 * 3 + SIZE * SIZE + 32 + 8 + 6  # 9710, SURVEY 8d / DESIGN.md
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU (weak scaling)")
+    ap.add_argument("--layouts", type=int, default=8192, help="layout pool size per GPU")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        self.t0 = time.time()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half by power draw (the sampler also sees setup / idle time)
+        order = sorted(range(len(sm)), key=lambda i: pw[i])
+        loaded = [sm[i] for i in order[len(order) // 2:]]
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU paths
+_W = {}
+
+
+def _cpu_worker_init(seed):
+    from oracle import merlin_ref as mr
+    env = mr.make_env("mediumhard", size=SIZE)
+    env.reset(seed=777_000_000 + seed)
+    import numpy as np
+    _W["env"], _W["rng"] = env, np.random.default_rng(seed)
+
+
+def _cpu_worker_run(n):
+    """n env-steps of the reference-style path (literal minigrid restatement + RGB/Img/ThreeAction wrappers),
+    random actions, reset on done -- what src/ppo.py:70-98 does per step minus the policy."""
+    if "env" not in _W:
+        _cpu_worker_init(os.getpid() % 100000)
+    env, rng = _W["env"], _W["rng"]
+    t0 = time.perf_counter()
+    for _ in range(n):
+        _, _, te, tr, _ = env.step(int(rng.integers(0, 3)))
+        if te or tr:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+class CpuReference:
+    """All host cores, one env per process (the reference has no vector env)."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_cpu_worker_run, [20] * self.cores)  # build envs + tile cache
+
+    def run(self, steps_per_proc):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker_run, [steps_per_proc] * self.cores, chunksize=1)
+        dt = time.perf_counter() - t0
+        return self.cores * steps_per_proc, dt
+
+    def close(self):
+        self.pool.terminate()
+
+
+def c_oracle_rate(seconds=3.0):
+    """Optimised C oracle (OpenMP over envs), NOT the reference: a second CPU data point."""
+    import numpy as np
+    from merlin_b200 import codes, layouts
+    from oracle import fast
+    cells, agent = layouts.generate("mediumhard", SIZE, range(777_000_000, 777_000_000 + 256))
+    N = 8192
+    env = fast.OracleVecEnv(N, codes.unpack_to_encoding(cells, SIZE, SIZE), agent)
+    env.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 3, (8, N))
+    env.step(acts[0])
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        env.step(acts[n % 8]); n += 1
+    return N * n / (time.perf_counter() - t0), fast.set_threads(0)
+
+
+def run_reference(args):
+    """--impl reference: the CPU path only, same metric/config; under torchrun rank 0 alone works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    ref = CpuReference()
+    n, dt = ref.run(200)  # calibrate
+    rate = n / dt
+    budget = 90.0  # seconds for warmup + steps
+    per_proc = max(5, int(rate * budget / max(1, args.steps + args.warmup) / ref.cores))
+    for _ in range(args.warmup):
+        ref.run(per_proc)
+    total, t = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = ref.run(per_proc)
+        total += n; t += dt
+    ref.close()
+    value = total / t
+    sample = (f"{args.steps} steps x {ref.cores} procs x {per_proc} env-steps each "
+              f"({total} env-steps, {t:.1f} s) of mediumhard 16x16 random-action stepping with reset on done")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "mediumhard 16x16, random actions, one env per host process (reference has no vector env)",
+                   "grid": SIZE, "obs": "u8[56,56,3] RGB POV", "actions": 3,
+                   "note": "upstream minigrid/gymnasium not installable: literal restatement (oracle port) + reference wrapper stack"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU path
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except (OSError, KeyError, ValueError):
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(envs):
+    """DRAM bytes per launch of the step kernel from the committed ncu --set full capture, if it matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            t = json.load(f)
+        if int(t.get("envs", -1)) == envs:
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from merlin_b200 import BatchedMerlinEnv, layouts
+
+    N, K, W = args.envs, args.steps, max(3, args.warmup)
+    # synthetic seeded layouts, a distinct slice of seeds per rank (seeds 777e6 + l)
+    base = 777_000_000 + rank * args.layouts
+    cells, agent = layouts.generate("mediumhard", SIZE, range(base, base + args.layouts))
+    env = BatchedMerlinEnv(N, cells, agent, width=SIZE, height=SIZE, device=dev, want_symbolic=False)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(777 + rank)
+    ring = 64
+    acts = torch.randint(0, 3, (ring, N), generator=g, device=dev)  # outside the timed region
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(W):
+        env.step(acts[i % ring])
+    barrier()
+    launches0 = env.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        env.step(acts[i % ring])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = env.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host action buffers -> step -> host reward/flags (observations stay in HBM) -------------------
+    e2e = None
+    if not args.skip_e2e:
+        Ke = min(K, 256)
+        h_ring = 8
+        h_act = torch.randint(0, 3, (h_ring, N), dtype=torch.int64).pin_memory()
+        d_act = torch.empty(N, dtype=torch.int64, device=dev)
+        h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+        h_te = torch.empty(N, dtype=torch.bool).pin_memory()
+        h_tr = torch.empty(N, dtype=torch.bool).pin_memory()
+
+        def e2e_step(i, h_obs=None):
+            d_act.copy_(h_act[i % h_ring], non_blocking=True)
+            obs, r, te, tr, _ = env.step(d_act)
+            h_rew.copy_(r, non_blocking=True); h_te.copy_(te, non_blocking=True); h_tr.copy_(tr, non_blocking=True)
+            if h_obs is not None:
+                h_obs.copy_(obs, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller owns the results on the host now
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            e2e_step(i)
+        barrier()
+        dt = time.perf_counter() - t0
+        # variant with every observation copied to the host as well (what a host-side consumer would need)
+        Ko = min(K, 4)
+        n_host = min(N, 1 << 17)  # bound pinned memory: copy the first 131072 frames (1.2 GB) and scale
+        h_obs = torch.empty((n_host, 56, 56, 3), dtype=torch.uint8).pin_memory()
+        barrier()
+        t1 = time.perf_counter()
+        for i in range(Ko):
+            d_act.copy_(h_act[i % h_ring], non_blocking=True)
+            obs, r, te, tr, _ = env.step(d_act)
+            h_rew.copy_(r, non_blocking=True)
+            for lo in range(0, N, n_host):
+                h_obs[: min(n_host, N - lo)].copy_(obs[lo:lo + n_host], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        barrier()
+        dt_obs = time.perf_counter() - t1
+        e2e = {"seconds": dt, "steps": Ke, "seconds_obs": dt_obs, "steps_obs": Ko}
+
+    # ---- reduce over ranks: max time, rank 0 prints -----------------------------------------------------------
+    times = torch.tensor([ms, e2e["seconds"] if e2e else 0.0, e2e["seconds_obs"] if e2e else 0.0], device=dev,
+                         dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_s, e2e_obs_s = [float(x) for x in times.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_steps = world * N * K
+    value = total_steps / (ms_max * 1e-3)
+    peak, peak_src = hbm_peak()
+    kernel_ms = ms_max / K
+    achieved = ALGO_BYTES_PER_STEP * N / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"configs[1]: mediumhard {SIZE}x{SIZE}, {N} envs per GPU, uniform random actions over "
+                               "{left,right,forward}, auto-reset, RGB obs u8[N,56,56,3]",
+                   "envs_per_gpu": N, "grid": SIZE, "max_steps": 4 * SIZE * SIZE, "layout_pool": args.layouts,
+                   "layout_seeds": f"{base}..{base + args.layouts - 1} (np.random.default_rng, host-generated, uploaded)",
+                   "parallelism": f"env-sharded x{world}, no data-path collective",
+                   "l2": f"per-step working set {N * ALGO_BYTES_PER_STEP / 1e9:.2f} GB written/read >> 126 MB L2 (inputs larger than L2)"},
+        "clocks": clocks,
+        "gpu_launches": int(launches) * world,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(N), "peak_source": peak_src, "kernel": "merlin::env_kernel<32,true>",
+                     "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "env_steps_per_launch": N,
+                     "launch_ms": kernel_ms},
+    }
+    if e2e:
+        h2d = N * 8
+        d2h = N * (4 + 1 + 1)
+        line["e2e"] = {"value": world * N * e2e["steps"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "obs_resident_in_hbm": True, "steps": e2e["steps"],
+                       "value_obs_to_host": world * N * e2e["steps_obs"] / e2e_obs_s,
+                       "d2h_bytes_per_step_obs_to_host": N * (56 * 56 * 3 + 4)}
+    if not args.skip_cpu_baseline:
+        ref = CpuReference()
+        n, dt = ref.run(200)
+        per_proc = max(50, int(n / dt * args.cpu_seconds / ref.cores))
+        n, dt = ref.run(per_proc)
+        ref.close()
+        c_rate, c_threads = c_oracle_rate()
+        line["cpu_baseline"] = {
+            "value": n / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
+            "sample": f"{n} env-steps ({ref.cores} procs x {per_proc}) in {dt:.1f} s, mediumhard 16x16 random actions, "
+                      "literal minigrid-3.0.0 restatement + reference wrapper stack (upstream not installable)",
+            "c_oracle_value": c_rate, "c_oracle_threads": c_threads,
+            "c_oracle_note": "optimised C restatement (OpenMP), not the reference"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
