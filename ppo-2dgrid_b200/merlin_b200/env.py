@@ -30,7 +30,7 @@ class BatchedMerlinEnv:
         agent: i32[L, 3] = (x, y, dir).  `reset_mode`: "next" advances each env's pool cursor by num_envs at
         every restart (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
         self.device = torch.device(device)
-        if self.device.type != "cuda":
+        if self.device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("BatchedMerlinEnv needs a CUDA device (no CPU fallback)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())

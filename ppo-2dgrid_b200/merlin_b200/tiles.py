@@ -117,15 +117,15 @@ def _draw_object(img, x, y, type_, color):
         raise ValueError(f"no renderer for type {type_}")
 
 
-def render_tile(type_, color, agent=False, highlight=False, tile=TILE):
+def render_tile(type_, color, agent=False, highlight=False, tile=TILE, agent_dir=3):
     n = tile * SUBDIVS
     x, y = _sample_grid(n)
     img = np.zeros((n, n, 3), dtype=np.uint8)
     _paint(img, _rect(x, y, 0, 0.031, 0, 1), (100, 100, 100))
     _paint(img, _rect(x, y, 0, 1, 0, 0.031), (100, 100, 100))
     _draw_object(img, x, y, type_, color)
-    if agent:  # agent_dir = 3 in a POV frame: rotate sample points by -theta about the centre, then test
-        theta = 0.5 * math.pi * 3
+    if agent:  # agent_dir is 3 in a POV frame: rotate sample points by -theta about the centre, then test
+        theta = 0.5 * math.pi * agent_dir
         xs, ys = x - 0.5, y - 0.5
         x2 = 0.5 + xs * math.cos(-theta) - ys * math.sin(-theta)
         y2 = 0.5 + ys * math.cos(-theta) + xs * math.sin(-theta)

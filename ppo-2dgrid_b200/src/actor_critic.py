@@ -1,0 +1,98 @@
+"""Actor-critic networks (PyTorch; out of the CUDA hot-path scope, kept so the drop-in is runnable).
+
+Architecture, initialisation and state_dict keys follow the reference (src/actor_critic.py:5-99) so that
+checkpoints are interchangeable: two separate Nature-CNN trunks (conv 8/4 -> 4/2 -> 3/1, ReLU) + 512-wide
+heads for images `[N, H, W, 3]`, a 64-64 tanh MLP pair for flat observations.  Unlike the reference the
+image path accepts the device-resident uint8 frames of the batched env directly (cast + /255 on the fly).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .utils.utils_rl import layer_init
+
+
+def _conv_stack(channels):
+    return nn.Sequential(
+        layer_init(nn.Conv2d(channels, 32, kernel_size=8, stride=4)), nn.ReLU(),
+        layer_init(nn.Conv2d(32, 64, kernel_size=4, stride=2)), nn.ReLU(),
+        layer_init(nn.Conv2d(64, 64, kernel_size=3, stride=1)), nn.ReLU(),
+        nn.Flatten(),
+    )
+
+
+class CNNFeatureExtractor(nn.Module):
+    def __init__(self, channels, height, width):
+        super().__init__()
+        self.network = _conv_stack(channels)
+        with torch.no_grad():
+            self.output_dim = self.network(torch.zeros(1, channels, height, width)).shape[1]
+
+    def forward(self, x):
+        return self.network(x / 255.0)
+
+
+def _head(in_dim, hidden, out_dim, out_std, act):
+    return nn.Sequential(layer_init(nn.Linear(in_dim, hidden)), act(), layer_init(nn.Linear(hidden, out_dim), std=out_std))
+
+
+class _ActorCriticBase(nn.Module):
+    """Shared act/evaluate on top of `_logits_value(obs)`.  Sampling, log-probabilities and entropy are the
+    categorical-distribution formulas written out on tensors (no distribution object, no argument validation),
+    so that a whole rollout can be captured in a CUDA graph without a host synchronisation."""
+
+    def forward(self, obs):
+        """(logits `[B, A]`, value `[B]`) -- the functional entry point used for stacked per-task weights."""
+        return self._logits_value(obs)
+
+    def act(self, obs, deterministic=False):
+        logits, value = self._logits_value(obs)
+        logp_all = torch.log_softmax(logits, dim=-1)
+        if deterministic:
+            action = torch.argmax(logits, dim=1)
+        else:
+            action = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
+        return action, logp_all.gather(-1, action.unsqueeze(-1)).squeeze(-1), value
+
+    def evaluate(self, obs, actions):
+        logits, value = self._logits_value(obs)
+        logp_all = torch.log_softmax(logits, dim=-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1)
+        return logp_all.gather(-1, actions.long().unsqueeze(-1)).squeeze(-1), entropy, value
+
+
+class CNNActorCritic(_ActorCriticBase):
+    def __init__(self, obs_shape, act_dim, hidden_dim=512):
+        super().__init__()
+        h, w, c = obs_shape
+        self.actor_extractor = CNNFeatureExtractor(c, h, w)
+        self.critic_extractor = CNNFeatureExtractor(c, h, w)
+        self.actor = _head(self.actor_extractor.output_dim, hidden_dim, act_dim, 0.01, nn.ReLU)
+        self.critic = _head(self.critic_extractor.output_dim, hidden_dim, 1, 1.0, nn.ReLU)
+
+    def _format_obs(self, x):
+        if x.ndim == 4 and x.shape[-1] == 3:  # NHWC (uint8 frames from the env, or float copies) -> NCHW float
+            return x.permute(0, 3, 1, 2).float()
+        return x.float()
+
+    def _logits_value(self, obs):
+        obs = self._format_obs(obs)
+        return self.actor(self.actor_extractor(obs)), self.critic(self.critic_extractor(obs)).squeeze(-1)
+
+
+class MLPActorCritic(_ActorCriticBase):
+    def __init__(self, obs_dim, act_dim, hidden_dim=64):
+        super().__init__()
+
+        def tower(out_dim, out_std):
+            return nn.Sequential(layer_init(nn.Linear(obs_dim, hidden_dim)), nn.Tanh(),
+                                 layer_init(nn.Linear(hidden_dim, hidden_dim)), nn.Tanh(),
+                                 layer_init(nn.Linear(hidden_dim, out_dim), std=out_std))
+
+        self.actor = tower(act_dim, 0.01)
+        self.critic = tower(1, 1.0)
+
+    def _logits_value(self, obs):
+        obs = obs.float()
+        return self.actor(obs), self.critic(obs).squeeze(-1)

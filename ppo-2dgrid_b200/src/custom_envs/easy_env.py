@@ -1,0 +1,7 @@
+"""EasyEnv: the `easy` MERLIN layout family (reference src/custom_envs/easy_env.py; layout routine restated on
+arrays in merlin_b200.layouts, same RNG draw order), stepped by the CUDA env kernels."""
+from .base_env import BaseCustomEnv
+
+
+class EasyEnv(BaseCustomEnv):
+    difficulty = "easy"

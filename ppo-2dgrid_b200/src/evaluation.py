@@ -1,0 +1,80 @@
+"""Batched deterministic evaluation -- one env per task seed, all tasks in flight at once.
+
+Batched core of the reference's evaluation loops, which run one seed after another with batch-1 inference:
+`evaluate_policy` (ppo/ppo_train.py:43-69: `episodes` seeds `seed + ep`), `evaluate_model`
+(src/sweep_checkpoints.py:58-78: seeds 200000..), `collect_zero_shot_metrics`
+(ppo/analyze_ppo_distribution.py:70-94) and `evaluate_zero_shot` (src/distribution_over_tasks.py:71-96).
+Each seed's layout is what `env.reset(seed=s)` builds; the policy acts greedily (`argmax`); an env's first
+episode is recorded when it ends (its return and length come from the step kernel's episode counters) and the
+env is ignored afterwards ("freeze after done").  The host looks at the device only every `poll` steps.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from merlin_b200 import BatchedMerlinEnv
+from merlin_b200 import layouts as _layouts
+
+
+@torch.no_grad()
+def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=None, deterministic=True, poll=64,
+                   env=None):
+    """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)])."""
+    seeds = [int(s) for s in seeds]
+    B = len(seeds)
+    cells, agent = _layouts.generate(difficulty, size, seeds)
+    if env is None or env.num_envs != B:
+        env = BatchedMerlinEnv(B, cells, agent, width=size, height=size, max_steps=max_steps, device=device,
+                               reset_mode="same", want_symbolic=False)
+    else:
+        env.upload_layouts(cells, agent)
+    env.set_cursors(np.arange(B, dtype=np.int32))
+    dev = env.device
+    ret = torch.zeros(B, dtype=torch.float32, device=dev)
+    length = torch.zeros(B, dtype=torch.int32, device=dev)
+    goal = torch.zeros(B, dtype=torch.bool, device=dev)
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    obs, _ = env.reset()
+    was_training = policy.training
+    policy.eval()
+    for t in range(env.max_steps):
+        action = policy.act(obs, deterministic=deterministic)[0]
+        obs, _, term, _, info = env.step(action)
+        first = (info["episode_length"] > 0) & ~finished
+        ret = torch.where(first, info["episode_return"], ret)
+        length = torch.where(first, info["episode_length"], length)
+        goal |= first & term
+        finished |= first
+        if (t + 1) % poll == 0 and bool(finished.all()):
+            break
+    policy.train(was_training)
+    return ret.double().cpu().numpy(), length.long().cpu().numpy(), goal.cpu().numpy()
+
+
+def evaluate_policy(agent, env_or_creator, episodes=3, seed=None, difficulty=None):
+    """Signature of ppo/ppo_train.py:43 -- `(rewards, steps_list)` for seeds `seed + ep`.  `env_or_creator` may be a
+    ScenarioCreator (then `difficulty` names the scenario), a BatchedMerlinEnv, or a reference-style single env."""
+    base = seed if seed is not None else 0
+    seeds = [base + ep for ep in range(episodes)]
+    if hasattr(env_or_creator, "create_batched_env"):
+        sc = env_or_creator
+        from src.custom_envs.register import DIFFICULTY_OF
+        diff = DIFFICULTY_OF[sc.get_env_id(difficulty)]
+        size = int(sc.config["difficulties"][difficulty].get("params", {}).get("size", 16))
+    elif isinstance(env_or_creator, BatchedMerlinEnv):
+        diff, size = env_or_creator.difficulty, env_or_creator.size
+    else:
+        u = env_or_creator.unwrapped
+        diff, size = u.difficulty, u.size
+    r, n, _ = evaluate_seeds(agent.ac, diff, size, seeds, device=agent.device if agent.device.type == "cuda" else "cuda")
+    return r.tolist(), n.tolist()
+
+
+def evaluate_model(sc, policy, difficulty, seeds, device="cuda"):
+    """src/sweep_checkpoints.py:58-78 -- (mean reward, mean steps) over `seeds`."""
+    from src.custom_envs.register import DIFFICULTY_OF
+    diff = DIFFICULTY_OF[sc.get_env_id(difficulty)]
+    size = int(sc.config["difficulties"][difficulty].get("params", {}).get("size", 16))
+    r, n, _ = evaluate_seeds(policy, diff, size, seeds, device=device)
+    return float(np.mean(r)), float(np.mean(n))

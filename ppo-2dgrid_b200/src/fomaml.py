@@ -1,0 +1,265 @@
+"""FOMAML with task-batched, device-resident rollouts (reference src/fomaml.py:8-223: same constructor,
+methods, attributes, hyper-parameters and loss; the data path is rewired).
+
+The reference adapts one task at a time: a batch-1 policy forward and one Python env step per transition.
+Here all tasks of a meta-batch advance together: task b is env b of one BatchedMerlinEnv (`reset_mode="same"`:
+a finished episode restarts on the task's own layout, src/fomaml.py:92), the support phase is a single batched
+forward of the shared meta-policy per step, and after the inner SGD step the per-task fast weights are a stacked
+parameter set evaluated with `torch.func.functional_call` under `vmap` (one grouped convolution for all tasks).
+GAE for all tasks is one launch of the CUDA kernel over the `[k, B]` rollout (gamma 0.995, lambda 0.95), followed
+by the reference's normalise-then-add returns convention (src/fomaml.py:126-127).  With `torch.distributed`
+initialised each rank adapts its shard of `task_seeds`; the accumulated first-order meta-gradient is
+all-reduced (SUM) once and divided by the GLOBAL task count (src/fomaml.py:207-209).
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.optim as optim
+from torch.func import functional_call, vmap
+
+from merlin_b200 import BatchedMerlinEnv, gae as gae_kernel
+from merlin_b200 import layouts as _layouts
+
+from . import parallel
+from .actor_critic import CNNActorCritic, MLPActorCritic
+
+
+class FOMAML:
+    def __init__(self, scenario_creator, lr_inner=0.01, lr_outer=3e-4, device="cpu", difficulty="medium"):
+        self.sc = scenario_creator
+        self.difficulty = difficulty
+        self.device = torch.device(device)
+        self.lr_inner = lr_inner
+
+        cfg = self.sc.config["difficulties"].get(difficulty)
+        if not cfg:
+            raise ValueError(f"Unknown difficulty: {difficulty}")
+        self.size = int({**self.sc.global_cfg, **cfg.get("params", {})}.get("size", 16))
+        if self.sc.obs_cfg.get("flatten", False):
+            self.use_cnn = False
+            self.meta_policy = MLPActorCritic(56 * 56 * 3, 3).to(self.device)
+        else:
+            self.use_cnn = True
+            self.meta_policy = CNNActorCritic((56, 56, 3), 3).to(self.device)
+        parallel.broadcast_parameters(self.meta_policy)
+        self.meta_optimizer = optim.Adam(self.meta_policy.parameters(), lr=lr_outer)
+        self.fast_policy = deepcopy(self.meta_policy).to(self.device)
+        self.fast_policy.train()
+
+        self.gamma = 0.995
+        self.lam = 0.95
+        self.vf_coef = 0.5
+        self.ent_coef = 0.05
+        self.clip_eps = 0.2
+        self._envs = {}  # task-batch size -> cached BatchedMerlinEnv
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def _obs_to_tensor(self, state):
+        state_t = torch.as_tensor(state, device=self.device).to(torch.float32)
+        return state_t.unsqueeze(0) if self.use_cnn else state_t.view(1, -1)
+
+    def _fmt(self, obs):
+        return obs if self.use_cnn else obs.reshape(obs.shape[0], -1)
+
+    def _task_env(self, task_seeds):
+        """One env per task seed, loaded with the layout `env.reset(seed=s)` would build."""
+        seeds = [int(s) for s in task_seeds]
+        cells, agent = _layouts.generate(self.sc_difficulty(), self.size, seeds)
+        B = len(seeds)
+        env = self._envs.get(B)
+        if env is None:
+            dev = self.device if self.device.type == "cuda" else "cuda"
+            env = BatchedMerlinEnv(B, cells, agent, width=self.size, height=self.size, device=dev, reset_mode="same",
+                                   want_symbolic=False)
+            self._envs[B] = env
+        else:
+            env.upload_layouts(cells, agent)
+        env.set_cursors(np.arange(B, dtype=np.int32))
+        return env
+
+    def sc_difficulty(self):
+        from src.custom_envs.register import DIFFICULTY_OF
+        return DIFFICULTY_OF[self.sc.get_env_id(self.difficulty)]
+
+    # ---- rollouts -----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def collect_trajectory(self, env, policy, steps=20, task_seed=None, params=None):
+        """`steps` transitions from a fresh reset.  `env`: a BatchedMerlinEnv whose B envs are B tasks (`policy`
+        acts for all of them; `params` = stacked per-task weights evaluates task b with its own weights), or a
+        reference-style single env (then `task_seed` re-seeds every reset, as in the reference).
+        Returns the reference's dict; batched tensors are time-major `[steps, B, ...]`."""
+        if not isinstance(env, BatchedMerlinEnv):
+            return self._collect_single(env, policy, steps, task_seed)
+        B, dev = env.num_envs, env.device
+        obs = torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev)
+        act = torch.empty((steps, B), dtype=torch.long, device=dev)
+        rew = torch.empty((steps, B), dtype=torch.float32, device=dev)
+        val = torch.empty_like(rew)
+        logp = torch.empty_like(rew)
+        done = torch.empty_like(rew)
+        ep_ret = torch.empty_like(rew)
+        ep_len = torch.empty((steps, B), dtype=torch.int32, device=dev)
+        env.reset(out_obs=obs[0])
+        for t in range(steps):
+            a, lp, v = self._act(policy, params, obs[t])
+            _, r, te, tr, info = env.step(a, out_obs=obs[t + 1])
+            act[t], logp[t], val[t], rew[t] = a, lp, v, r
+            done[t] = (te | tr).float()
+            ep_ret[t], ep_len[t] = info["episode_return"], info["episode_length"]
+        last_val = self._act(policy, params, obs[steps])[2]
+        ended = ep_len > 0
+        return {"obs": obs[:steps], "act": act, "rew": rew, "val": val, "logp": logp, "done": done,
+                "last_val": last_val, "ep_lens": ep_len[ended].tolist(), "ep_rews": ep_ret[ended].tolist()}
+
+    def _act(self, policy, params, obs):
+        """Sampled action, its log-probability and the value for one frame per task."""
+        if params is None:
+            return policy.act(self._fmt(obs), deterministic=False)
+        logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
+        logits, value = logits.squeeze(1), value.squeeze(1)
+        logp_all = torch.log_softmax(logits, dim=-1)
+        a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
+        return a, logp_all.gather(-1, a.unsqueeze(-1)).squeeze(-1), value
+
+    def _collect_single(self, env, policy, steps, task_seed):
+        obs_buf, act_buf, rew_buf, val_buf, logp_buf, done_buf = [], [], [], [], [], []
+        ep_lens, ep_rews, cur_len, cur_rew = [], [], 0, 0
+        state, _ = env.reset(seed=task_seed)
+        for _ in range(steps):
+            state_t = self._obs_to_tensor(state)
+            action, logp, value = policy.act(state_t, deterministic=False)
+            state, reward, terminated, truncated, _ = env.step(action.item())
+            done = terminated or truncated
+            cur_len += 1
+            cur_rew += reward
+            obs_buf.append(state_t); act_buf.append(action); rew_buf.append(reward)
+            val_buf.append(value); logp_buf.append(logp); done_buf.append(done)
+            if done:
+                ep_lens.append(cur_len); ep_rews.append(cur_rew)
+                cur_len, cur_rew = 0, 0
+                state, _ = env.reset(seed=task_seed)
+        last_val = policy.act(self._obs_to_tensor(state))[2]
+        return {"obs": torch.cat(obs_buf), "act": torch.cat(act_buf),
+                "rew": torch.tensor(rew_buf, dtype=torch.float32).to(self.device), "val": torch.cat(val_buf),
+                "logp": torch.cat(logp_buf), "done": torch.tensor(done_buf, dtype=torch.float32).to(self.device),
+                "last_val": last_val, "ep_lens": ep_lens, "ep_rews": ep_rews}
+
+    # ---- loss ---------------------------------------------------------------------------------------------
+    def _advantages(self, batch):
+        """GAE kernel over `[k]` or `[k, B]`, then per-task normalisation and `ret = val + adv_norm`."""
+        rew, val, done = batch["rew"], batch["val"], batch["done"]
+        dev = rew.device
+        g = dev if dev.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        last = batch["last_val"]
+        last = last.reshape(-1).to(g) if torch.is_tensor(last) else float(last)
+        adv, _ = gae_kernel(rew.to(g), val.to(g), done.to(g), last, self.gamma, self.lam)
+        adv = adv.to(dev)
+        adv = (adv - adv.mean(0, keepdim=True)) / (adv.std(0, keepdim=True) + 1e-8)
+        return adv, (val + adv).detach()
+
+    def compute_loss(self, batch, policy, params=None):
+        """PPO-clip loss of the reference (src/fomaml.py:110-156).  Single trajectory -> (loss, stats) as in the
+        reference.  Task-batched trajectory (`[k, B]`) -> (per-task loss `[B]`, stats averaged over tasks); with
+        `params` (stacked per-task weights) task b is evaluated under its own weights."""
+        adv, ret = self._advantages(batch)
+        old_logp = batch["logp"].detach()
+        obs, act = batch["obs"], batch["act"]
+        if adv.dim() == 1:
+            new_logp, entropy, new_vals = policy.evaluate(obs, act)
+        elif params is None:
+            k, B = act.shape
+            new_logp, entropy, new_vals = policy.evaluate(self._fmt(obs.reshape((k * B,) + obs.shape[2:])), act.reshape(-1))
+            new_logp, entropy, new_vals = new_logp.view(k, B), entropy.view(k, B), new_vals.view(k, B)
+        else:
+            obs_b = self._fmt_tasks(obs)  # [B, k, ...]
+            logits, vals = vmap(lambda p, o: _logits_value(policy, p, o))(params, obs_b)
+            logp_all = torch.log_softmax(logits, dim=-1)  # [B, k, A]
+            entropy = (-(logp_all.exp() * logp_all).sum(-1)).t()
+            new_logp = logp_all.gather(-1, act.t().unsqueeze(-1)).squeeze(-1).t()
+            new_vals = vals.t()
+        ratio = torch.exp(new_logp - old_logp)
+        surr = torch.min(ratio * adv, torch.clamp(ratio, 1.0 - self.clip_eps, 1.0 + self.clip_eps) * adv)
+        pi_loss = -surr.mean(0)
+        v_loss = ((new_vals - ret) ** 2).mean(0)
+        ent = entropy.mean(0)
+        total = pi_loss + self.vf_coef * v_loss - self.ent_coef * ent
+        with torch.no_grad():
+            kl = (old_logp - new_logp).mean()
+            clipfrac = (torch.abs(ratio - 1.0) > self.clip_eps).float().mean()
+            s = torch.stack([pi_loss.mean(), v_loss.mean(), ent.mean(), kl, clipfrac]).tolist()
+        stats = {"loss": total, "pi_loss": s[0], "v_loss": s[1], "entropy": s[2], "kl": s[3], "clipfrac": s[4]}
+        return total, stats
+
+    def _fmt_tasks(self, obs):
+        o = obs.transpose(0, 1)  # [B, k, 56, 56, 3]
+        return o if self.use_cnn else o.reshape(o.shape[0], o.shape[1], -1)
+
+    # ---- meta step ----------------------------------------------------------------------------------------
+    def meta_train_step(self, task_seeds, k_support=50, k_query=50):
+        task_seeds = list(task_seeds)
+        n_global = len(task_seeds)
+        my_seeds = parallel.shard(task_seeds)
+        meta = self.meta_policy
+        names = [n for n, _ in meta.named_parameters()]
+        self.meta_optimizer.zero_grad()
+        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        lens, rews, query_stats = [], [], {}
+        grads_sum = [torch.zeros_like(p) for p in meta.parameters()]
+
+        if my_seeds:
+            B = len(my_seeds)
+            env = self._task_env(my_seeds)
+            # inner loop: support rollout under the shared meta weights, one SGD step per task
+            support = self.collect_trajectory(env, meta, steps=k_support)
+            fast = {n: p.detach().unsqueeze(0).repeat((B,) + (1,) * p.dim()).requires_grad_(True)
+                    for n, p in meta.named_parameters()}
+            s_loss, _ = self.compute_loss(support, meta, params=fast)
+            g = torch.autograd.grad(s_loss.sum(), [fast[n] for n in names])
+            coef = _clip_coef(g, 0.5)
+            with torch.no_grad():
+                fast = {n: (fast[n] - self.lr_inner * gi * coef.view((B,) + (1,) * (gi.dim() - 1))).requires_grad_(True)
+                        for n, gi in zip(names, g)}
+            # outer loop: query rollout under each task's adapted weights, first-order gradient
+            query = self.collect_trajectory(env, meta, steps=k_query, params=fast)
+            lens, rews = query["ep_lens"], query["ep_rews"]
+            q_loss, query_stats = self.compute_loss(query, meta, params=fast)
+            gq = torch.autograd.grad(q_loss.sum(), [fast[n] for n in names])
+            grads_sum = [gi.sum(0) for gi in gq]
+            loss_sum = q_loss.detach().double().sum()
+            query_stats = {**query_stats, "loss": q_loss.detach().mean()}
+            with torch.no_grad():  # keep `fast_policy` = the last task's adapted weights, as the reference leaves it
+                for n, p in self.fast_policy.named_parameters():
+                    p.copy_(fast[n][-1])
+
+        # the one collective: SUM of the accumulated meta-gradient (and of the logged loss), then / global #tasks
+        flat = torch.cat([gi.reshape(-1) for gi in grads_sum] + [loss_sum.reshape(1).to(grads_sum[0].dtype)])
+        if parallel.world_size() > 1:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+        flat = flat / n_global
+        off = 0
+        for p in meta.parameters():
+            p.grad = flat[off: off + p.numel()].view_as(p).clone()
+            off += p.numel()
+        avg_loss = float(flat[off].item())
+        torch.nn.utils.clip_grad_norm_(meta.parameters(), max_norm=0.5)
+        self.meta_optimizer.step()
+
+        if len(rews) > 0:
+            avg_rew, avg_steps = float(np.mean(rews)), float(np.mean(lens))
+        else:
+            avg_rew, avg_steps = 0.0, float(k_query)
+        return avg_loss, avg_rew, avg_steps, query_stats
+
+
+def _logits_value(policy, params, obs):
+    """`policy._logits_value(obs)` evaluated with `params` substituted for the module's own weights."""
+    return functional_call(policy, params, (obs,))
+
+
+def _clip_coef(grads, max_norm):
+    """Per-task `clip_grad_norm_` coefficient for stacked gradients `[B, ...]` (src/fomaml.py:181)."""
+    sq = sum(g.reshape(g.shape[0], -1).pow(2).sum(1) for g in grads)
+    return torch.clamp(max_norm / (sq.sqrt() + 1e-6), max=1.0)

@@ -1,0 +1,206 @@
+"""PPO with device-resident rollouts (reference src/ppo.py:9-175: same constructor, methods, attributes and
+update math; only the data path is rewired).
+
+Two rollout paths behind `collect_rollouts()`:
+  * a BatchedMerlinEnv (N envs, one fused CUDA launch per step): observations are rendered by the env kernel
+    straight into the `[T, N, 56, 56, 3]` uint8 rollout buffer, actions come from one batched policy forward,
+    nothing crosses PCIe and nothing synchronises until the rollout is over; optionally the whole T-step loop
+    is replayed from one CUDA graph.  `batch_size` = T * N transitions per rollout.
+  * the reference's single-env wrapper stack (`ScenarioCreator.create_env`): the same per-step loop as the
+    reference (src/ppo.py:64-105), one env, host observations -- kept so existing scripts run unchanged.
+GAE always runs in the CUDA kernel (`merlin_b200.gae`).  With `torch.distributed` initialised, every rank rolls
+out its own envs and the flattened gradient is all-reduced once per minibatch step (src/parallel.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from merlin_b200 import BatchedMerlinEnv, gae as gae_kernel
+from src.metrics.ppo_metrics import aggregate_ppo_update_metrics
+
+from . import parallel
+from .actor_critic import CNNActorCritic, MLPActorCritic
+from .rollout_buffer import RolloutBuffer
+
+
+class PPO:
+    def __init__(self, env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
+                 minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False):
+        self.env = env
+        self.batched = isinstance(env, BatchedMerlinEnv)
+        self.device = env.device if self.batched else torch.device(device)
+        self.gamma, self.lam, self.clip_eps = gamma, lam, clip_eps
+        self.update_epochs, self.batch_size, self.minibatch_size = update_epochs, batch_size, minibatch_size
+        self.vf_coef, self.ent_coef = vf_coef, ent_coef
+
+        if self.batched:
+            self.num_envs = env.num_envs
+            act_dim = env.n_actions
+            self.use_cnn, self.obs_shape = True, tuple(env.obs.shape[1:])
+        else:
+            self.num_envs = 1
+            sample_obs, _ = env.reset()
+            act_dim = env.action_space.n
+            self.use_cnn = sample_obs.ndim != 1
+            self.obs_shape = tuple(sample_obs.shape) if self.use_cnn else (int(np.prod(sample_obs.shape)),)
+        if self.use_cnn:
+            self.ac = CNNActorCritic(self.obs_shape, act_dim).to(self.device)
+        else:
+            self.ac = MLPActorCritic(self.obs_shape[0], act_dim).to(self.device)
+        parallel.broadcast_parameters(self.ac)
+        self.optimizer = optim.Adam(self.ac.parameters(), lr=lr)
+        self._grads = FlatOrNone(self.ac) if parallel.world_size() > 1 else None
+
+        self.buffer = RolloutBuffer(buffer_size=self.batch_size, obs_shape=self.obs_shape, device=self.device,
+                                    is_discrete=True, num_envs=self.num_envs,
+                                    obs_dtype=torch.uint8 if self.batched else torch.float32)
+        self.episode_returns = []
+        self.episode_lengths = []
+
+        if self.batched:
+            T, N = self.buffer.horizon, self.num_envs
+            self._last_obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=self.device)
+            self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
+            self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
+            self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
+        self.use_cuda_graph = bool(use_cuda_graph) and self.batched
+        self._graph = None
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def _obs_to_tensor(self, state):
+        state_t = torch.as_tensor(state, device=self.device).to(torch.float32)
+        return state_t.unsqueeze(0) if self.use_cnn else state_t.view(1, -1)
+
+    def _gae_device(self):
+        return self.device if self.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+
+    # ---- rollouts -----------------------------------------------------------------------------------------
+    def collect_rollouts(self):
+        """One rollout of `batch_size` transitions; returns the bootstrap value (`float` for a single env, a
+        `[N]` device tensor for a batched env).  Like the reference it starts from a fresh `reset()`."""
+        return self._collect_batched() if self.batched else self._collect_single()
+
+    def _rollout_body(self):
+        env, buf, T = self.env, self.buffer, self.buffer.horizon
+        env.reset(out_obs=buf.obs_slot(0))
+        for t in range(T):
+            action, logp, value = self.ac.act(buf.obs_slot(t), deterministic=False)
+            nxt = buf.obs_slot(t + 1) if t + 1 < T else self._last_obs
+            _, rew, term, trunc, info = env.step(action, out_obs=nxt)
+            buf.actions[t].copy_(action)
+            buf.logprobs[t].copy_(logp)
+            buf.values[t].copy_(value)
+            buf.rewards[t].copy_(rew)
+            torch.logical_or(term, trunc, out=self._done_tmp)
+            buf.dones[t].copy_(self._done_tmp)
+            self._ep_ret[t].copy_(info["episode_return"])
+            self._ep_len[t].copy_(info["episode_length"])
+        self._last_value.copy_(self.ac.act(self._last_obs)[2])
+
+    @torch.no_grad()
+    def _collect_batched(self):
+        if not hasattr(self, "_done_tmp"):
+            self._done_tmp = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        if self.use_cuda_graph:
+            if self._graph is None:
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
+                    self.ac.act(self.buffer.obs_slot(0))
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._rollout_body()
+            self._graph.replay()
+        else:
+            self._rollout_body()
+        ended = self._ep_len > 0  # one synchronisation per rollout, for the episode logs
+        self.episode_returns.extend(self._ep_ret[ended].tolist())
+        self.episode_lengths.extend(self._ep_len[ended].tolist())
+        return self._last_value
+
+    def _collect_single(self):
+        state, _ = self.env.reset()
+        ep_return, ep_length = 0, 0
+        for _ in range(self.batch_size):
+            state_t = self._obs_to_tensor(state)
+            with torch.no_grad():
+                action, logp, value = self.ac.act(state_t, deterministic=False)
+            state, reward, terminated, truncated, _ = self.env.step(action.item())
+            done = terminated or truncated
+            self.buffer.add(state_t.squeeze(0), action.squeeze(), logp.squeeze(), value.squeeze(),
+                            torch.tensor(reward, dtype=torch.float32, device=self.device),
+                            torch.tensor(done, dtype=torch.float32, device=self.device))
+            ep_return += reward
+            ep_length += 1
+            if done:
+                self.episode_returns.append(ep_return)
+                self.episode_lengths.append(ep_length)
+                state, _ = self.env.reset()
+                ep_return, ep_length = 0, 0
+        with torch.no_grad():
+            return self.ac.act(self._obs_to_tensor(state))[2].item()
+
+    # ---- GAE ----------------------------------------------------------------------------------------------
+    def compute_gae(self, rewards, values, dones, last_value):
+        """`[T]` or time-major `[T, N]` tensors -> (adv, returns), computed by the CUDA GAE kernel."""
+        dev = rewards.device
+        g = self._gae_device()
+        adv, ret = gae_kernel(rewards.to(g), values.to(g), dones.to(g), last_value, self.gamma, self.lam)
+        return adv.to(dev), ret.to(dev)
+
+    # ---- update -------------------------------------------------------------------------------------------
+    def update(self, last_value):
+        states, actions, logprobs_old, rewards, values_old, dones = self.buffer.get()
+        adv, returns = self.compute_gae(rewards, values_old, dones, last_value)
+        mean, std = parallel.global_mean_std(adv)
+        adv = (adv - mean) / (std + 1e-8)
+
+        n = self.buffer.horizon * self.num_envs
+        states = states.reshape((n,) + self.obs_shape)
+        actions, logprobs_old = actions.reshape(n), logprobs_old.reshape(n)
+        adv, returns = adv.reshape(n), returns.reshape(n)
+
+        totals = torch.zeros(6, dtype=torch.float64, device=self.device)
+        nbatches = 0
+        for _ in range(self.update_epochs):
+            idxs = torch.randperm(n, device=self.device)
+            for start in range(0, n, self.minibatch_size):
+                mb = idxs[start: start + self.minibatch_size]
+                logp_new, entropy, values = self.ac.evaluate(states[mb], actions[mb])
+                mb_adv, mb_old = adv[mb], logprobs_old[mb]
+                ratio = torch.exp(logp_new - mb_old)
+                surr = torch.min(ratio * mb_adv, torch.clamp(ratio, 1 - self.clip_eps, 1 + self.clip_eps) * mb_adv)
+                pi_loss = -surr.mean()
+                v_loss = ((values - returns[mb]) ** 2).mean()
+                ent = entropy.mean()
+                loss = pi_loss + self.vf_coef * v_loss - self.ent_coef * ent
+
+                if self._grads is not None:
+                    self._grads.zero_()
+                else:
+                    self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                if self._grads is not None:
+                    self._grads.all_reduce_mean()
+                grad_norm = torch.nn.utils.clip_grad_norm_(self.ac.parameters(), 0.5)
+                self.optimizer.step()
+
+                with torch.no_grad():
+                    kl = (mb_old - logp_new).mean()
+                    clipfrac = (torch.abs(ratio - 1.0) > self.clip_eps).float().mean()
+                    totals += torch.stack([pi_loss, v_loss, ent, kl, clipfrac, grad_norm]).double()
+                nbatches += 1
+        return aggregate_ppo_update_metrics(*totals.tolist(), nbatches)  # the only host sync of the update
+
+    def train(self, total_steps=100_000):
+        steps_done = 0
+        while steps_done < total_steps:
+            self.update(self.collect_rollouts())
+            steps_done += self.batch_size * parallel.world_size()
+
+
+def FlatOrNone(module):
+    return parallel.FlatGrads(module.parameters())

@@ -16,12 +16,15 @@ Fixture format (all .npz, deflate-compressed):
   trace_<name>.npz                 per-episode layouts + per-step actions/obs/reward/flags/pose
   stuck_trace.npz                  StuckPenaltyWrapper rewards + info["stuck"]
   gae.npz                          inputs + (adv, returns) from the reference GAE loops
+  ppo_config1_rollout.npz          one reference PPO rollout (2048 steps, seed 777): layouts, actions, rewards, dones,
+                                   values, frame CRCs and the reference's own GAE output
 """
 from __future__ import annotations
 
 import os
 import sys
 import types
+import zlib
 from collections import deque
 
 import numpy as np
@@ -223,9 +226,68 @@ def gen_gae():
     np.savez_compressed(os.path.join(OUT, "gae.npz"), **out)
 
 
+class _Recorder:
+    """Transparent env proxy that snapshots the layout after every reset and the frame CRC of every step."""
+
+    def __init__(self, env):
+        self._env = env
+        self.enc, self.agent, self.reset_crc, self.step_crc = [], [], [], []
+
+    def __getattr__(self, name):
+        return getattr(self._env, name)
+
+    def reset(self, **kw):
+        obs, info = self._env.reset(**kw)
+        e, a = snapshot(self._env)
+        self.enc.append(e)
+        self.agent.append(a)
+        self.reset_crc.append(zlib.crc32(np.ascontiguousarray(obs).tobytes()))
+        return obs, info
+
+    def step(self, action):
+        out = self._env.step(action)
+        self.step_crc.append(zlib.crc32(np.ascontiguousarray(out[0]).tobytes()))
+        return out
+
+
+def gen_ppo_config1():
+    """BASELINE config 1, first iteration: the reference's own PPO.collect_rollouts + compute_gae
+    (src/ppo.py:64-120) on mediumhard 16x16 with `set_seed(777)` and the ppo_train.py defaults
+    (batch 2048, gamma .99, lambda .95), policy on the CPU.  The env RNG is seeded once (reset(seed=777)) because
+    the reference leaves it to OS entropy; every later reset continues that stream, as in training."""
+    from src.utils.utils import set_seed
+    set_seed(777)
+    sc = ScenarioCreator(YAML)
+    env = _Recorder(sc.create_env("mediumhard"))
+    env.reset(seed=777)
+    agent = PPO(env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
+                minibatch_size=256, vf_coef=0.5, ent_coef=0.05, device="cpu")
+    n_reset_before = len(env.enc)           # reset(seed) + PPO.__init__'s reset
+    last_value = agent.collect_rollouts()
+    states, actions, logp, rewards, values, dones = agent.buffer.get()
+    adv, ret = agent.compute_gae(rewards, values, dones, last_value)
+    np.savez_compressed(
+        os.path.join(OUT, "ppo_config1_rollout.npz"),
+        ep_enc=np.stack(env.enc), ep_agent=np.stack(env.agent), resets_before_rollout=n_reset_before,
+        reset_crc=np.array(env.reset_crc, dtype=np.uint32), step_crc=np.array(env.step_crc, dtype=np.uint32),
+        action=actions.numpy().astype(np.int64), reward=rewards.numpy(), done=dones.numpy(),
+        value=values.numpy(), logp=logp.numpy(), last_value=np.float64(last_value),
+        adv=adv.numpy(), ret=ret.numpy(), gamma=np.float64(0.99), lam=np.float64(0.95),
+        first_state_crc=np.uint32(zlib.crc32(states[0].numpy().astype(np.uint8).tobytes())),
+        episode_returns=np.array(agent.episode_returns, dtype=np.float64),
+        episode_lengths=np.array(agent.episode_lengths, dtype=np.int64),
+    )
+    print("ppo_config1: episodes", len(agent.episode_returns), "layouts", len(env.enc), "reward sum",
+          float(rewards.sum()), "dones", int(dones.sum()))
+
+
 if __name__ == "__main__":
+    if "--only-ppo" in sys.argv:
+        gen_ppo_config1()
+        sys.exit(0)
     gen_layouts()
     gen_traces()
     gen_gae()
+    gen_ppo_config1()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT) if f.endswith(".npz"))
     print("total fixture bytes", total)

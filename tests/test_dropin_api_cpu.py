@@ -1,0 +1,196 @@
+"""CPU tier: the drop-in Python surface of the reference (`src.*`) -- names, signatures, error behaviour and the
+host-side logic that needs no device (YAML table, registry, action map, rollout storage, rank sharding, the
+stacked-weight policy evaluation FOMAML uses).  Compute entry points must refuse to run without CUDA."""
+from __future__ import annotations
+
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import src  # noqa: F401  (product mirror on sys.path via conftest)
+from src import CNNActorCritic, MLPActorCritic, RolloutBuffer, get_device, layer_init  # reference src/__init__.py:1-4
+from src.fomaml import FOMAML, _clip_coef, _logits_value
+from src.ppo import PPO
+from src.scenario_creator.scenario_creator import ScenarioCreator
+from src.wrappers.stuck_penalty_wrapper import StuckPenaltyWrapper
+from src.wrappers.three_action_wrapper import ThreeActionWrapper
+
+
+def _params(fn):
+    return [p for p in inspect.signature(fn).parameters if p != "self"]
+
+
+def test_reference_signatures_are_kept():
+    # reference src/ppo.py:10-23, src/fomaml.py:9-16,54,110,158, src/rollout_buffer.py:4,15,24,
+    # src/scenario_creator/scenario_creator.py:11,35,59-73, src/wrappers/*.py
+    assert _params(PPO.__init__)[:11] == ["env", "lr", "gamma", "lam", "clip_eps", "update_epochs", "batch_size",
+                                          "minibatch_size", "vf_coef", "ent_coef", "device"]
+    d = {k: v.default for k, v in inspect.signature(PPO.__init__).parameters.items()}
+    assert (d["lr"], d["gamma"], d["lam"], d["clip_eps"], d["update_epochs"], d["batch_size"], d["minibatch_size"],
+            d["vf_coef"], d["ent_coef"], d["device"]) == (3e-4, 0.99, 0.95, 0.2, 10, 2048, 256, 0.5, 0.01, "cpu")
+    assert _params(PPO.compute_gae) == ["rewards", "values", "dones", "last_value"]
+    assert _params(PPO.update) == ["last_value"] and _params(PPO.train) == ["total_steps"]
+    assert hasattr(PPO, "collect_rollouts") and hasattr(PPO, "_obs_to_tensor")
+    assert _params(FOMAML.__init__) == ["scenario_creator", "lr_inner", "lr_outer", "device", "difficulty"]
+    assert _params(FOMAML.collect_trajectory)[:4] == ["env", "policy", "steps", "task_seed"]
+    assert _params(FOMAML.compute_loss)[:2] == ["batch", "policy"]
+    assert _params(FOMAML.meta_train_step) == ["task_seeds", "k_support", "k_query"]
+    assert _params(RolloutBuffer.__init__)[:4] == ["buffer_size", "obs_shape", "device", "is_discrete"]
+    assert _params(RolloutBuffer.add) == ["state", "action", "logprob", "value", "reward", "done"]
+    assert _params(ScenarioCreator.__init__) == ["config_path"]
+    assert _params(ScenarioCreator.create_env) == ["difficulty", "seed"]
+    assert _params(StuckPenaltyWrapper.__init__) == ["env", "max_stay", "penalty"]
+    assert _params(ThreeActionWrapper.__init__) == ["env"]
+    for name in ("sample_scenarios", "get_env_id", "get_logging_params", "get_observation_params", "get_env_size_str",
+                 "create_batched_env"):
+        assert hasattr(ScenarioCreator, name)
+
+
+def test_scenario_creator_yaml_and_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        ScenarioCreator(str(tmp_path / "nope.yaml"))
+    sc = ScenarioCreator()
+    assert sc.get_env_id("mediumhard") == "MERLIN-MediumHard-v0"
+    assert sc.get_env_size_str("hard") == "16x16"
+    assert sc.get_observation_params() == {"fully_observable": False, "flatten": False}
+    assert sc.seed == 42 and sc.global_cfg == {} and sc.get_logging_params() == {}
+    with pytest.raises(ValueError, match="Unknown difficulty"):
+        sc.create_env("impossible")
+    with pytest.raises(ValueError, match="Unknown difficulty"):
+        sc.create_batched_env("impossible", 4)
+    bad = tmp_path / "two_sizes.yaml"
+    bad.write_text("difficulties:\n  a: {env_id: MERLIN-16x16-v0}\n  b: {env_id: MERLIN-32x32-v0}\n")
+    with pytest.raises(ValueError, match="Multiple grid sizes"):
+        ScenarioCreator(str(bad))
+
+
+def test_registry_and_wrapper_stack_without_device():
+    import src.custom_envs.register as reg
+    assert set(reg.registry) == {"MERLIN-Easy-v0", "MERLIN-Medium-v0", "MERLIN-MediumHard-v0", "MERLIN-Hard-v0",
+                                 "MERLIN-Hardest-v0"}
+    with pytest.raises(KeyError):
+        reg.make("MERLIN-Nope-v0")
+    env = ScenarioCreator().create_env("mediumhard", seed=5)
+    assert env.action_space.n == 3
+    assert env.observation_space.shape == (56, 56, 3)
+    u = env.unwrapped
+    assert (u.max_steps, u.width, u.height, u.agent_view_size, u.see_through_walls) == (1024, 16, 16, 7, False)
+    assert [int(env.action(a)) for a in (0, 1, 2)] == [int(u.actions.left), int(u.actions.right), int(u.actions.forward)]
+    assert len(u.actions) == 7 and u.action_space.n == 7
+    with pytest.raises(RuntimeError):
+        env.step(0)  # before reset
+    big = ScenarioCreator()
+    big.config["difficulties"]["hard"]["params"]["size"] = 32
+    assert big.create_env("hard").unwrapped.max_steps == 4 * 32 * 32  # base_env.py:32-33
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_compute_paths_refuse_to_run_without_cuda():
+    env = ScenarioCreator().create_env("easy")
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        env.reset(seed=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ScenarioCreator().create_batched_env("easy", 8, seeds=range(8))
+    from merlin_b200 import gae
+    with pytest.raises(RuntimeError, match="GPU only"):
+        gae(torch.zeros(4), torch.zeros(4), torch.zeros(4), 0.0)
+
+
+def test_rollout_buffer_reference_semantics():
+    buf = RolloutBuffer(4, (2, 2, 3), "cpu", is_discrete=True)
+    assert buf.states.shape == (4, 2, 2, 3) and buf.states.dtype == torch.float32
+    assert buf.actions.dtype == torch.long and buf.max_size == 4 and buf.ptr == 0
+    for k in range(5):  # wraps like the reference ring (src/rollout_buffer.py:15-22)
+        buf.add(torch.full((2, 2, 3), float(k)), torch.tensor(k % 3), torch.tensor(-0.1 * k), torch.tensor(0.5 * k),
+                torch.tensor(float(k)), torch.tensor(float(k == 2)))
+    assert buf.ptr == 1
+    states, actions, logp, rew, val, done = buf.get()
+    assert buf.ptr == 0
+    assert states[0, 0, 0, 0] == 4 and actions.tolist() == [1, 1, 2, 0] and rew.tolist() == [4, 1, 2, 3]
+    assert done.tolist() == [0, 0, 1, 0] and val[3] == 1.5 and abs(float(logp[1]) + 0.1) < 1e-7
+    cont = RolloutBuffer(4, (3,), "cpu", is_discrete=False)
+    assert cont.actions.dtype == torch.float32
+
+
+def test_rollout_buffer_batched_time_major():
+    buf = RolloutBuffer(6 * 5, (56, 56, 3), "cpu", num_envs=5, obs_dtype=torch.uint8)
+    assert buf.horizon == 6 and buf.states.shape == (6, 5, 56, 56, 3) and buf.states.dtype == torch.uint8
+    slot = buf.obs_slot(2)
+    slot.fill_(7)  # what the env kernel does through out_obs
+    buf.ptr = 2
+    buf.add(None, torch.arange(5), torch.zeros(5), torch.ones(5), torch.full((5,), 2.0), torch.zeros(5))
+    assert buf.states[2].min() == 7 and buf.actions[2].tolist() == [0, 1, 2, 3, 4] and buf.rewards[2, 4] == 2
+    assert slot.data_ptr() == buf.states[2].data_ptr() and slot.is_contiguous()
+    with pytest.raises(ValueError):
+        RolloutBuffer(7, (3,), "cpu", num_envs=2)
+    one = RolloutBuffer(3, (56, 56, 3), "cpu", num_envs=1, obs_dtype=torch.uint8)
+    assert one.obs_slot(1).shape == (1, 56, 56, 3) and one.obs_slot(1).data_ptr() == one.states[1].data_ptr()
+
+
+def test_actor_critic_state_dict_keys_and_math():
+    torch.manual_seed(0)
+    ac = CNNActorCritic((56, 56, 3), 3)
+    keys = set(ac.state_dict())
+    # checkpoint compatibility with reference src/actor_critic.py (module names and Sequential indices)
+    for k in ("actor_extractor.network.0.weight", "actor_extractor.network.2.weight", "actor_extractor.network.4.bias",
+              "critic_extractor.network.0.weight", "actor.0.weight", "actor.2.bias", "critic.0.weight", "critic.2.weight"):
+        assert k in keys, k
+    assert sum(p.numel() for p in ac.parameters()) == 744_772
+    obs_u8 = torch.randint(0, 256, (5, 56, 56, 3), dtype=torch.uint8)
+    a, logp, v = ac.act(obs_u8)
+    a2, logp2, v2 = ac.act(obs_u8.float(), deterministic=True)
+    assert a.shape == logp.shape == v.shape == (5,) and torch.allclose(v, v2)
+    dist = torch.distributions.Categorical(logits=ac(obs_u8)[0])
+    lp, ent, val = ac.evaluate(obs_u8, a)
+    assert torch.allclose(lp, dist.log_prob(a), atol=1e-6) and torch.allclose(ent, dist.entropy(), atol=1e-6)
+    assert torch.equal(a2, ac(obs_u8)[0].argmax(1))
+    mlp = MLPActorCritic(12, 3)
+    assert mlp.act(torch.zeros(2, 12))[0].shape == (2,)
+    assert get_device("cpu").type == "cpu" and callable(layer_init)
+
+
+def test_stacked_weights_match_per_task_modules():
+    """FOMAML's vmap(functional_call) path == running each task's own module; per-task clip == clip_grad_norm_."""
+    torch.manual_seed(1)
+    pol = CNNActorCritic((56, 56, 3), 3)
+    B, k = 3, 4
+    mods = [CNNActorCritic((56, 56, 3), 3) for _ in range(B)]
+    stacked = {n: torch.stack([dict(m.named_parameters())[n].detach() for m in mods]).requires_grad_(True)
+               for n, _ in pol.named_parameters()}
+    obs = torch.randint(0, 256, (B, k, 56, 56, 3), dtype=torch.uint8)
+    lg, v = torch.func.vmap(lambda p, o: _logits_value(pol, p, o))(stacked, obs)
+    loss = (lg.pow(2).sum((1, 2)) + v.pow(2).sum(1))
+    grads = torch.autograd.grad(loss.sum(), list(stacked.values()))
+    coef = _clip_coef(grads, 0.5)
+    for b, m in enumerate(mods):
+        l2, v2 = m(obs[b])
+        assert torch.allclose(lg[b], l2, atol=1e-5) and torch.allclose(v[b], v2, atol=1e-5)
+        m.zero_grad()
+        (l2.pow(2).sum() + v2.pow(2).sum()).backward()
+        ref = [p.grad.clone() for p in m.parameters()]
+        for gs, gr in zip(grads, ref):
+            assert torch.allclose(gs[b], gr, rtol=1e-4, atol=1e-5)
+        total = torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
+        assert abs(float(coef[b]) - min(1.0, 0.5 / (float(total) + 1e-6))) < 1e-5
+
+
+def test_shard_is_balanced_and_covers_everything():
+    from src import parallel
+    for n in (0, 1, 7, 32, 33):
+        for w in (1, 2, 3, 8):
+            parts = [parallel.shard(range(n), r, w) for r in range(w)]
+            assert sum(parts, []) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert parallel.world_size() == 1 and parallel.rank() == 0
+
+
+def test_metrics_helpers():
+    from src.metrics.ppo_metrics import aggregate_ppo_update_metrics, compute_episode_stats
+    assert aggregate_ppo_update_metrics(1, 2, 3, 4, 5, 6, 0)["kl"] == 0.0
+    assert aggregate_ppo_update_metrics(2, 4, 6, 8, 10, 12, 2) == {"pi_loss": 1, "v_loss": 2, "entropy": 3, "kl": 4,
+                                                                    "clipfrac": 5, "gradnorm": 6}
+    assert compute_episode_stats([], []) == {"episode_return_mean": 0.0, "episode_length_mean": 0.0}
+    assert compute_episode_stats([1.0, 0.0], [10, 30]) == {"episode_return_mean": 0.5, "episode_length_mean": 20.0}

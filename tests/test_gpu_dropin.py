@@ -1,0 +1,268 @@
+"""GPU tier: the reference-facing Python surface (`src.*`) running on the CUDA path, checked against the golden
+fixtures produced by the reference's own code and against the oracle.
+
+  * `ScenarioCreator.create_env` wrapper stack replays the reference traces bit-exactly FROM THE SEED (layout
+    generation + step + observation), including StuckPenaltyWrapper.
+  * BASELINE config 1: the first rollout of the reference's own PPO (seed 777) is replayed through the CUDA env with
+    the recorded actions -- rewards, dones and every 56x56x3 frame (CRC) are identical; the GAE kernel reproduces the
+    reference's advantages/returns.
+  * batched PPO / FOMAML: rollouts stored on the device are self-consistent with the oracle env driven by the stored
+    actions; updates run and change the weights; CUDA-graph rollouts equal eager rollouts in distribution checks.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import fast
+
+pytestmark = pytest.mark.gpu
+
+
+def _sc():
+    from src.scenario_creator.scenario_creator import ScenarioCreator
+    return ScenarioCreator()
+
+
+def _crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes())
+
+
+# ---- single-env wrapper stack, from the seed --------------------------------------------------------------
+@pytest.mark.parametrize("name", helpers.trace_names())
+def test_create_env_replays_reference_trace_from_seed(name):
+    from src.wrappers.stuck_penalty_wrapper import StuckPenaltyWrapper
+    tr = helpers.load(f"trace_{name}.npz")
+    sc = _sc()
+    diff, size = str(tr["difficulty"]), int(tr["size"])
+    sc.config["difficulties"][diff]["params"]["size"] = size
+    env = sc.create_env(diff)
+    if bool(tr["stuck_wrapper"]):
+        env = StuckPenaltyWrapper(env)
+    obs, info = env.reset(seed=int(tr["seed"]))
+    u = env.unwrapped
+    if int(tr["max_steps"]) != u.max_steps:
+        pytest.skip("fixture overrides max_steps after construction")
+    assert obs.dtype == np.uint8 and obs.shape == (56, 56, 3) and info == {}
+    assert np.array_equal(obs, tr["reset_obs_rgb"][0])
+    assert np.array_equal(u.grid.encode(), tr["ep_enc"][0])
+    assert (u.agent_pos[0], u.agent_pos[1], u.agent_dir) == tuple(tr["ep_agent"][0])
+    for t, a in enumerate(tr["action"]):
+        obs, r, te, tr_, info = env.step(int(a))
+        assert isinstance(r, float) and isinstance(te, bool) and isinstance(tr_, bool)
+        assert np.array_equal(obs, tr["obs_rgb"][t]), t
+        assert np.float32(r) == np.float32(tr["reward"][t]), t
+        assert (te, tr_) == (bool(tr["terminated"][t]), bool(tr["truncated"][t])), t
+        assert (u.agent_pos[0], u.agent_pos[1], u.agent_dir, u.step_count) == tuple(tr["pose"][t]), t
+        if bool(tr["stuck_wrapper"]):
+            assert info["stuck"] == bool(tr["stuck"][t]), t
+        if te or tr_:
+            ep = int(tr["episode"][t]) + 1
+            obs, _ = env.reset()  # continues the env's RNG stream: next layout of the reference run
+            assert np.array_equal(obs, tr["reset_obs_rgb"][ep]), t
+            assert np.array_equal(u.grid.encode(), tr["ep_enc"][ep]), t
+    env.close()
+
+
+def test_single_env_surface_details():
+    sc = _sc()
+    env = sc.create_env("mediumhard", seed=3)
+    o1, _ = env.reset(seed=11)
+    o2, _ = env.reset(seed=11)  # FOMAML re-seeds at every reset (src/fomaml.py:63,92): same task again
+    assert np.array_equal(o1, o2)
+    with pytest.raises(ValueError, match="Unknown action"):
+        env.unwrapped.step(9)
+    frame = env.unwrapped.get_frame()  # fomaml_train.py:107
+    assert frame.shape == (16 * 32, 16 * 32, 3) and frame.dtype == np.uint8
+    pov = env.unwrapped.get_frame(tile_size=8, agent_pov=True)
+    assert np.array_equal(pov, o2)
+    # full frame against the literal renderer of the oracle
+    from oracle import merlin_ref as mr
+    ref = mr.make_env("mediumhard", size=16)
+    ref.reset(seed=11)
+    assert np.array_equal(frame, ref.unwrapped.get_frame(True, 32, False))
+    env.step(1)
+    ref.step(1)
+    assert np.array_equal(env.unwrapped.get_frame(), ref.unwrapped.get_frame(True, 32, False))
+    env.close()
+
+
+# ---- BASELINE config 1: the reference's own PPO rollout ------------------------------------------------------
+def test_config1_reference_ppo_rollout_replayed_on_gpu():
+    from merlin_b200 import BatchedMerlinEnv, gae
+    fx = helpers.load("ppo_config1_rollout.npz")
+    k0 = int(fx["resets_before_rollout"])  # reset(seed) and PPO.__init__'s reset happen before the rollout
+    env = BatchedMerlinEnv(1, enc=fx["ep_enc"], agent=fx["ep_agent"], device="cuda:0", auto_reset=False,
+                           reset_mode="next")
+    for k in range(k0 + 1):  # ... and collect_rollouts() starts with its own reset (src/ppo.py:65)
+        obs, _ = env.reset()
+        assert _crc(obs[0].cpu().numpy()) == int(fx["reset_crc"][k])
+    assert _crc(obs[0].cpu().numpy()) == int(fx["first_state_crc"])
+    ep, rewards, dones, ep_ret, ep_len, rets, lens = k0, [], [], 0.0, 0, [], []
+    for t, a in enumerate(fx["action"]):
+        obs, r, te, tr, _ = env.step(torch.tensor([int(a)], device="cuda:0"))
+        assert _crc(obs[0].cpu().numpy()) == int(fx["step_crc"][t]), t
+        done = bool(te[0]) or bool(tr[0])
+        rewards.append(float(r[0]))
+        dones.append(float(done))
+        ep_ret += float(r[0])
+        ep_len += 1
+        if done:
+            rets.append(ep_ret)
+            lens.append(ep_len)
+            ep_ret, ep_len = 0.0, 0
+            ep += 1
+            obs, _ = env.reset()
+            assert _crc(obs[0].cpu().numpy()) == int(fx["reset_crc"][ep]), t
+    assert np.array_equal(np.float32(rewards), fx["reward"]) and np.array_equal(np.float32(dones), fx["done"])
+    assert lens == fx["episode_lengths"].tolist() and np.allclose(rets, fx["episode_returns"], atol=1e-6)
+    dev = "cuda:0"
+    adv, ret = gae(torch.tensor(fx["reward"], device=dev), torch.tensor(fx["value"], device=dev),
+                   torch.tensor(fx["done"], device=dev), float(fx["last_value"]), float(fx["gamma"]), float(fx["lam"]))
+    assert np.array_equal(adv.cpu().numpy(), fx["adv"]) and np.array_equal(ret.cpu().numpy(), fx["ret"])
+
+
+# ---- batched PPO ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("graph", [False, True])
+def test_batched_ppo_rollout_is_consistent_with_oracle_and_updates(graph):
+    from merlin_b200 import codes, layouts
+    from src.ppo import PPO
+    torch.manual_seed(5)
+    N, T, L = 64, 12, 256
+    sc = _sc()
+    env = sc.create_batched_env("mediumhard", N, device="cuda:0", seeds=range(500, 500 + L), max_steps=9)
+    agent = PPO(env, batch_size=N * T, minibatch_size=256, update_epochs=2, ent_coef=0.05, use_cuda_graph=graph)
+    assert agent.buffer.states.shape == (T, N, 56, 56, 3) and agent.buffer.states.dtype == torch.uint8
+    before = [p.detach().clone() for p in agent.ac.parameters()]
+    cells, ag = layouts.generate("mediumhard", 16, range(500, 500 + L))
+    ref = fast.OracleVecEnv(N, codes.unpack_to_encoding(cells, 16, 16), ag, max_steps=9)
+    n_eps = 0
+    for it in range(2):  # with graph=True the second call replays the captured graph
+        last_value = agent.collect_rollouts()
+        assert last_value.shape == (N,)
+        states, actions, logp, rewards, values, dones = agent.buffer.get()
+        assert torch.isfinite(logp).all() and torch.isfinite(values).all()
+        nxt = torch.cat([states[1:], agent._last_obs.unsqueeze(0)]).cpu().numpy()
+        # every rollout starts from a fresh reset of all envs on their next layouts (src/ppo.py:65); the oracle
+        # follows the same cursor rule, so it can be driven with the stored actions across both rollouts
+        robs, _ = ref.reset()
+        assert np.array_equal(states[0].cpu().numpy(), robs), it
+        acts = actions.cpu().numpy()
+        for t in range(T):
+            robs, rr, rte, rtr, rinfo = ref.step(acts[t])
+            assert np.array_equal(rewards[t].cpu().numpy(), rr), (it, t)
+            assert np.array_equal(dones[t].cpu().numpy(), (rte | rtr).astype(np.float32)), (it, t)
+            assert np.array_equal(nxt[t], robs), (it, t)
+            n_eps += int((rinfo["episode_length"] > 0).sum())
+        assert int(dones.sum()) >= N  # max_steps 9 < T: every env truncates at least once
+    assert len(agent.episode_lengths) == len(agent.episode_returns) == n_eps
+    assert all(0 < l <= 9 for l in agent.episode_lengths)
+    adv, ret = agent.compute_gae(rewards, values, dones, last_value)
+    radv, rret = fast.gae(rewards.cpu().numpy(), values.cpu().numpy(), dones.cpu().numpy(), last_value.cpu().numpy(),
+                          0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), radv) and np.array_equal(ret.cpu().numpy(), rret)
+    m = agent.update(last_value)
+    assert set(m) == {"pi_loss", "v_loss", "entropy", "kl", "clipfrac", "gradnorm"}
+    assert all(np.isfinite(v) for v in m.values()) and 0.5 < m["entropy"] <= np.log(3) + 1e-5
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, agent.ac.parameters()))
+
+
+def test_batched_ppo_stored_logp_and_values_match_evaluate():
+    from src.ppo import PPO
+    torch.manual_seed(1)
+    env = _sc().create_batched_env("medium", 32, device="cuda:0", seeds=range(64))
+    agent = PPO(env, batch_size=32 * 4, minibatch_size=64, update_epochs=1)
+    agent.collect_rollouts()
+    s, a, logp, r, v, d = agent.buffer.get()
+    with torch.no_grad():
+        lp, _, val = agent.ac.evaluate(s.reshape(-1, 56, 56, 3), a.reshape(-1))
+    assert torch.allclose(lp.view_as(logp), logp, atol=1e-5) and torch.allclose(val.view_as(v), v, atol=1e-4)
+    agent.train(total_steps=2 * 32 * 4)  # reference PPO.train loop
+
+
+def test_single_env_ppo_reference_loop_runs_on_the_cuda_env():
+    from src.ppo import PPO
+    torch.manual_seed(0)
+    env = _sc().create_env("medium")
+    env.reset(seed=4)
+    agent = PPO(env, batch_size=64, minibatch_size=32, update_epochs=1, device="cuda:0")
+    assert agent.buffer.states.shape == (64, 56, 56, 3) and agent.buffer.states.dtype == torch.float32
+    lv = agent.collect_rollouts()
+    assert isinstance(lv, float)
+    m = agent.update(lv)
+    assert np.isfinite(m["pi_loss"]) and np.isfinite(m["gradnorm"])
+    adv, ret = agent.compute_gae(agent.buffer.rewards, agent.buffer.values, agent.buffer.dones, lv)
+    radv, rret = fast.gae(agent.buffer.rewards.cpu().numpy()[:, None], agent.buffer.values.cpu().numpy()[:, None],
+                          agent.buffer.dones.cpu().numpy()[:, None], np.float32([lv]), 0.99, 0.95)
+    assert np.allclose(adv.cpu().numpy(), radv[:, 0], rtol=1e-6, atol=1e-7)
+    assert np.allclose(ret.cpu().numpy(), rret[:, 0], rtol=1e-6, atol=1e-7)
+    env.close()
+
+
+# ---- FOMAML ---------------------------------------------------------------------------------------------------
+def test_fomaml_task_batched_meta_step_matches_per_task_loop():
+    from merlin_b200 import codes, layouts
+    from src.fomaml import FOMAML
+    torch.manual_seed(3)
+    sc = _sc()
+    fo = FOMAML(sc, lr_inner=0.01, lr_outer=3e-4, device="cuda:0", difficulty="mediumhard")
+    assert (fo.gamma, fo.lam, fo.vf_coef, fo.ent_coef, fo.clip_eps) == (0.995, 0.95, 0.5, 0.05, 0.2)
+    seeds = [7, 11, 100003, 5]
+    B, k = len(seeds), 24
+    # (a) trajectories: task b == env b, restarted on its own layout; frames/rewards reproducible by the oracle
+    env = fo._task_env(seeds)
+    traj = fo.collect_trajectory(env, fo.meta_policy, steps=k)
+    assert traj["obs"].shape == (k, B, 56, 56, 3) and traj["act"].shape == (k, B) and traj["last_val"].shape == (B,)
+    cells, ag = layouts.generate("mediumhard", 16, seeds)
+    ref = fast.OracleVecEnv(B, codes.unpack_to_encoding(cells, 16, 16), ag, reset_mode="same")
+    robs, _ = ref.reset()
+    assert np.array_equal(traj["obs"][0].cpu().numpy(), robs)
+    for t in range(k):
+        robs, rr, rte, rtr, _ = ref.step(traj["act"][t].cpu().numpy())
+        assert np.array_equal(traj["rew"][t].cpu().numpy(), rr)
+        assert np.array_equal(traj["done"][t].cpu().numpy(), (rte | rtr).astype(np.float32))
+        if t + 1 < k:
+            assert np.array_equal(traj["obs"][t + 1].cpu().numpy(), robs)
+    # (b) task-batched loss under stacked weights == the reference-style per-task loss on each column
+    meta = fo.meta_policy
+    fast_w = {n: p.detach().unsqueeze(0).repeat((B,) + (1,) * p.dim()).requires_grad_(True)
+              for n, p in meta.named_parameters()}
+    loss_b, stats = fo.compute_loss(traj, meta, params=fast_w)
+    assert loss_b.shape == (B,)
+    for b in range(B):
+        single = {"obs": traj["obs"][:, b].float(), "act": traj["act"][:, b], "rew": traj["rew"][:, b],
+                  "val": traj["val"][:, b], "logp": traj["logp"][:, b], "done": traj["done"][:, b],
+                  "last_val": traj["last_val"][b]}
+        l1, s1 = fo.compute_loss(single, meta)
+        assert abs(float(l1) - float(loss_b[b])) < 2e-4 * max(1.0, abs(float(l1))), (b, float(l1), float(loss_b[b]))
+        # advantages: kernel vs the reference's numpy loop restated in the oracle (normalise, then ret = val + adv)
+        from oracle import merlin_ref as mr
+        _, adv_ref, ret_ref = mr.gae_fomaml(single["rew"].cpu().numpy(), single["val"].cpu().numpy(),
+                                         single["done"].cpu().numpy(), float(single["last_val"]), 0.995, 0.95)
+        adv_k, ret_k = fo._advantages(single)
+        assert np.allclose(adv_k.cpu().numpy(), adv_ref, rtol=1e-5, atol=1e-6)
+        assert np.allclose(ret_k.cpu().numpy(), ret_ref, rtol=1e-5, atol=1e-6)
+    # (c) a full meta step moves the meta weights and reports finite numbers
+    before = [p.detach().clone() for p in meta.parameters()]
+    avg_loss, avg_rew, avg_steps, qstats = fo.meta_train_step(seeds, k_support=k, k_query=k)
+    assert np.isfinite(avg_loss) and np.isfinite(avg_rew) and avg_steps > 0
+    assert {"pi_loss", "v_loss", "entropy", "kl", "clipfrac", "loss"} <= set(qstats)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, meta.parameters()))
+    assert all(torch.isfinite(p).all() for p in meta.parameters())
+
+
+def test_fomaml_single_env_reference_path():
+    from src.fomaml import FOMAML
+    torch.manual_seed(0)
+    sc = _sc()
+    fo = FOMAML(sc, device="cuda:0", difficulty="medium")
+    env = sc.create_env("medium", seed=9)
+    batch = fo.collect_trajectory(env, fo.fast_policy, steps=16, task_seed=9)
+    assert batch["obs"].shape == (16, 56, 56, 3) and batch["rew"].shape == (16,)
+    loss, stats = fo.compute_loss(batch, fo.fast_policy)
+    assert loss.dim() == 0 and np.isfinite(float(loss)) and np.isfinite(stats["kl"])
+    env.close()
