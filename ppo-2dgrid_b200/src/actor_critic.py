@@ -22,15 +22,39 @@ def _conv_stack(channels):
     )
 
 
+def space_to_depth4(frames):
+    """`[N, H, W, C]` frames (uint8 from the env, or float) -> float `[N, 16*C, H/4, W/4]` in channels-last memory:
+    every 4x4 pixel block becomes one position with channel index `c*16 + dy*4 + dx`."""
+    n, h, w, c = frames.shape
+    x = frames.reshape(n, h // 4, 4, w // 4, 4, c).permute(0, 1, 3, 5, 2, 4).reshape(n, h // 4, w // 4, c * 16)
+    return x.permute(0, 3, 1, 2).float()
+
+
+def _space_to_depth4_weight(weight):
+    """The `[O, C, 8, 8]` stride-4 kernel as the equivalent `[O, 16*C, 2, 2]` stride-1 kernel over space_to_depth4."""
+    o, c, _, _ = weight.shape
+    return weight.reshape(o, c, 2, 4, 2, 4).permute(0, 1, 3, 5, 2, 4).reshape(o, c * 16, 2, 2)
+
+
 class CNNFeatureExtractor(nn.Module):
     def __init__(self, channels, height, width):
         super().__init__()
         self.network = _conv_stack(channels)
         with torch.no_grad():
             self.output_dim = self.network(torch.zeros(1, channels, height, width)).shape[1]
+        self.blockable = height % 4 == 0 and width % 4 == 0
 
     def forward(self, x):
+        """x: `[N, C, H, W]` float pixel values in 0..255 (the reference's input convention)."""
         return self.network(x / 255.0)
+
+    def forward_blocked(self, xb):
+        """Same function on `space_to_depth4` input.  The first layer (8x8, stride 4, 3 input channels) is evaluated
+        as a 2x2 stride-1 convolution over 48 channels with the SAME parameters (re-indexed on the fly, 1/255 folded
+        into them): identical sums in a different order, and a shape cuDNN runs several times faster than C = 3."""
+        conv1 = self.network[0]
+        h = torch.nn.functional.conv2d(xb, _space_to_depth4_weight(conv1.weight) * (1.0 / 255.0), conv1.bias)
+        return self.network[1:](h)
 
 
 def _head(in_dim, hidden, out_dim, out_std, act):
@@ -71,14 +95,21 @@ class CNNActorCritic(_ActorCriticBase):
         self.actor = _head(self.actor_extractor.output_dim, hidden_dim, act_dim, 0.01, nn.ReLU)
         self.critic = _head(self.critic_extractor.output_dim, hidden_dim, 1, 1.0, nn.ReLU)
 
+        self.blocked_first_layer = self.actor_extractor.blockable  # False: evaluate conv1 literally (8x8, stride 4)
+
     def _format_obs(self, x):
         if x.ndim == 4 and x.shape[-1] == 3:  # NHWC (uint8 frames from the env, or float copies) -> NCHW float
             return x.permute(0, 3, 1, 2).float()
         return x.float()
 
     def _logits_value(self, obs):
-        obs = self._format_obs(obs)
-        return self.actor(self.actor_extractor(obs)), self.critic(self.critic_extractor(obs)).squeeze(-1)
+        if self.blocked_first_layer and obs.ndim == 4 and obs.shape[-1] == 3:
+            xb = space_to_depth4(obs)  # shared by both trunks
+            fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
+        else:
+            obs = self._format_obs(obs)
+            fa, fc = self.actor_extractor(obs), self.critic_extractor(obs)
+        return self.actor(fa), self.critic(fc).squeeze(-1)
 
 
 class MLPActorCritic(_ActorCriticBase):

@@ -194,3 +194,21 @@ def test_metrics_helpers():
                                                                     "clipfrac": 5, "gradnorm": 6}
     assert compute_episode_stats([], []) == {"episode_return_mean": 0.0, "episode_length_mean": 0.0}
     assert compute_episode_stats([1.0, 0.0], [10, 30]) == {"episode_return_mean": 0.5, "episode_length_mean": 20.0}
+
+
+def test_blocked_first_layer_is_the_same_function():
+    """conv1 as a 2x2/stride-1 conv over space_to_depth4 input == the literal 8x8/stride-4 conv (same parameters)."""
+    torch.manual_seed(4)
+    ac = CNNActorCritic((56, 56, 3), 3)
+    obs = torch.randint(0, 256, (6, 56, 56, 3), dtype=torch.uint8)
+    assert ac.blocked_first_layer
+    l1, v1 = ac(obs)
+    g1 = torch.autograd.grad(l1.pow(2).sum() + v1.sum(), list(ac.parameters()))
+    ac.blocked_first_layer = False
+    l2, v2 = ac(obs)
+    g2 = torch.autograd.grad(l2.pow(2).sum() + v2.sum(), list(ac.parameters()))
+    assert torch.allclose(l1, l2, atol=1e-5) and torch.allclose(v1, v2, atol=1e-5)
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+    l3, v3 = ac(obs.float())  # float NHWC copies (the reference's buffer dtype) take the same path
+    assert torch.allclose(l3, l2, atol=1e-6)

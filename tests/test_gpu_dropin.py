@@ -266,3 +266,28 @@ def test_fomaml_single_env_reference_path():
     loss, stats = fo.compute_loss(batch, fo.fast_policy)
     assert loss.dim() == 0 and np.isfinite(float(loss)) and np.isfinite(stats["kl"])
     env.close()
+
+
+# ---- batched deterministic evaluation ----------------------------------------------------------
+def test_batched_evaluation_matches_sequential_reference_loop():
+    """evaluate_seeds == the reference's one-seed-at-a-time greedy loop (ppo/ppo_train.py:43-69) run on the oracle env
+    with the same policy."""
+    from oracle import merlin_ref as mr
+    from src.actor_critic import CNNActorCritic
+    from src.evaluation import evaluate_seeds
+    torch.manual_seed(2)
+    policy = CNNActorCritic((56, 56, 3), 3).to("cuda:0")
+    seeds = [200000, 200001, 200002, 7, 8]
+    ret, length, goal = evaluate_seeds(policy, "medium", 8, seeds, device="cuda:0", poll=16)
+    for k, s in enumerate(seeds):
+        env = mr.make_env("medium", size=8)
+        obs, _ = env.reset(seed=s)
+        done, total, steps, te = False, 0.0, 0, False
+        while not done:
+            with torch.no_grad():
+                a = policy.act(torch.as_tensor(obs, device="cuda:0").unsqueeze(0), deterministic=True)[0]
+            obs, r, te, tr, _ = env.step(int(a.item()))
+            total += r
+            steps += 1
+            done = te or tr
+        assert steps == int(length[k]) and abs(total - ret[k]) < 1e-6 and bool(goal[k]) == bool(te), (s, steps, length[k])

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""GAE kernel timing: algorithmic bytes (20 B per (t, env) + 4 B per env) / CUDA-event time, against the measured HBM
+peak, at the training size (T=128, N=4096: launch-bound) and at streaming sizes (N*T >= 2^26), beside the reference's
+Python loop (src/ppo.py:107-120) restated in the oracle, on the CPU.
+
+    python tools/bench_gae.py --out profiles/r01_gae.json
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "ppo-2dgrid_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    import torch
+    from merlin_b200 import gae
+
+    dev = torch.device("cuda", 0)
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    rows = []
+    for T, N in [(2048, 1), (128, 4096), (128, 65536), (128, 524288), (1024, 65536), (64, 1048576), (256, 1048576)]:
+        rew = torch.rand(T, N, device=dev)
+        val = torch.randn(T, N, device=dev)
+        done = (torch.rand(T, N, device=dev) < 0.01).float()
+        last = torch.randn(N, device=dev)
+        for _ in range(3):
+            gae(rew, val, done, last)
+        torch.cuda.synchronize()
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gae(rew, val, done, last)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps  # includes the two output allocations of the host wrapper
+        nbytes = 20 * T * N + 4 * N
+        rows.append({"T": T, "N": N, "ms": ms, "algorithmic_mb": nbytes / 1e6, "achieved_gbs": nbytes / ms / 1e6,
+                     "frac_of_hbm_peak": nbytes / ms / 1e6 / peak})
+        print(json.dumps(rows[-1]), flush=True)
+        del rew, val, done, last
+    # the reference loop (0-dim torch tensors, CPU) on one env, T = 2048
+    from oracle import merlin_ref as mr
+    T = 2048
+    r, v, d = torch.rand(T), torch.randn(T), (torch.rand(T) < 0.01).float()
+    t0 = time.perf_counter()
+    mr.gae_ppo(r, v, d, 0.3, 0.99, 0.95)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out = {"what": "GAE + returns kernel", "hbm_peak_gbs": peak, "rows": rows,
+           "cpu_reference_loop": {"T": T, "N": 1, "ms": cpu_ms, "kind": "port of src/ppo.py:107-120 (torch CPU)"}}
+    print(json.dumps(out["cpu_reference_loop"]))
+    if a.out:
+        with open(a.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

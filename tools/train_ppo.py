@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--layouts", type=int, default=65536)
     ap.add_argument("--eval-tasks", type=int, default=100)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="also time one reference-style PPO iteration (N=1, 2048 steps) on the host cores (oracle port)")
     ap.add_argument("--out", default=None)
     ap.add_argument("--save", default=None, help="path for the final state_dict (.pth, reference format)")
     a = ap.parse_args()
@@ -125,6 +127,16 @@ def main():
                "eval": {"tasks": a.eval_tasks, "seeds": "200000..", "mean_return": float(np.mean(r)),
                         "mean_steps": float(np.mean(n)), "success_rate": float(np.mean(g)), "eval_s": te},
                "train_log": log[:: max(1, len(log) // 20)] + log[-1:]}
+        if a.cpu_baseline:
+            from oracle import ppo_ref
+            cb = ppo_ref.cpu_ppo_sps(a.difficulty, 16, a.seed, update_budget_s=30.0)
+            out["cpu_baseline"] = {
+                "value": cb["steps_per_s"], "unit": "env-steps/s", "cores": cb["torch_threads"], "kind": "port",
+                "sample": f"one PPO iteration of the reference regime (1 env x 2048 steps, batch-1 inference, 10 epochs x 8 "
+                          f"minibatches of 256): rollout {cb['rollout_s']:.1f} s + update {cb['update_s']:.1f} s "
+                          f"({cb['minibatches_run']}/{cb['minibatches_total']} minibatch steps measured); literal minigrid "
+                          "restatement + reference wrapper stack, torch CPU",
+                "projected_wall_s_for_total_steps": iters * steps_per_iter / cb["steps_per_s"]}
         print(json.dumps(out), flush=True)
         if a.out:
             os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
