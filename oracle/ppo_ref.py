@@ -115,3 +115,58 @@ def cpu_ppo_sps(difficulty="mediumhard", size=16, seed=777, update_budget_s=20.0
     res["steps_per_s"] = res["steps"] / (res["rollout_s"] + res["update_s"])
     res["torch_threads"] = torch.get_num_threads()
     return res
+
+
+# ---- FOMAML: one task of a meta-iteration, reference style -------------------------------------------------------
+def _fomaml_traj(env, net, k, seed):
+    """src/fomaml.py:54-108 -- k single-env steps, batch-1 inference, `reset(seed=seed)` after every done."""
+    obs, _ = env.reset(seed=seed)
+    O, A, LP, V, R, D = [], [], [], [], [], []
+    for _ in range(k):
+        x = torch.tensor(obs, dtype=torch.float32).unsqueeze(0)
+        with torch.no_grad():
+            dist, v = net.dist_value(x)
+            a = dist.sample()
+        obs, r, te, tr, _ = env.step(a.item())
+        O.append(x); A.append(a); LP.append(dist.log_prob(a)); V.append(v); R.append(r); D.append(te or tr)
+        if te or tr:
+            obs, _ = env.reset(seed=seed)
+    with torch.no_grad():
+        last = net.dist_value(torch.tensor(obs, dtype=torch.float32).unsqueeze(0))[1]
+    return (torch.cat(O), torch.cat(A), torch.cat(LP), torch.cat(V), torch.tensor(R, dtype=torch.float32),
+            torch.tensor(D, dtype=torch.float32), last)
+
+
+def _fomaml_loss(net, traj, gamma=0.995, lam=0.95, clip=0.2, vf=0.5, ent=0.05):
+    """src/fomaml.py:110-156 -- numpy GAE loop, normalise, ret = val + adv_norm, PPO-clip loss."""
+    O, A, LP, V, R, D, last = traj
+    _, adv_n, ret = mr.gae_fomaml(R.numpy(), V.numpy(), D.numpy(), last.item(), gamma, lam)
+    adv_n, ret = torch.tensor(adv_n), torch.tensor(ret)
+    dist, v = net.dist_value(O)
+    lp = dist.log_prob(A)
+    ratio = torch.exp(lp - LP)
+    pi = -torch.min(ratio * adv_n, torch.clamp(ratio, 1 - clip, 1 + clip) * adv_n).mean()
+    return pi + vf * ((v - ret) ** 2).mean() - ent * dist.entropy().mean()
+
+
+def cpu_fomaml_task_seconds(difficulty="mediumhard", size=16, k=256, seed=123, threads=None):
+    """Wall seconds the reference-style loop spends on ONE task of a meta-iteration (support rollout + inner SGD step +
+    query rollout + query backward, src/fomaml.py:167-202) on this host; a meta-iteration is tasks_per_batch of these."""
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    env = mr.make_env(difficulty, size=size)
+    net = RefActorCritic(3)
+    inner = torch.optim.SGD(net.parameters(), lr=0.01)
+    _fomaml_traj(env, net, 8, seed)  # warm the tile cache / allocator
+    t0 = time.perf_counter()
+    loss = _fomaml_loss(net, _fomaml_traj(env, net, k, seed))
+    inner.zero_grad()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(net.parameters(), 0.5)
+    inner.step()
+    env.reset(seed=seed)
+    q = _fomaml_loss(net, _fomaml_traj(env, net, k, seed))
+    net.zero_grad()
+    q.backward()
+    return {"seconds_per_task": time.perf_counter() - t0, "k": k, "torch_threads": torch.get_num_threads()}

@@ -30,7 +30,7 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, ui
 }
 
 template <int G, bool STEP>
-__global__ void __launch_bounds__(kThreads) env_kernel(const EnvParams p, const int n_groups) {
+__global__ void __launch_bounds__(kThreads, MERLIN_MIN_BLOCKS) env_kernel(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const EnvParams p, const 
   const bool want_sym = p.obs_sym != nullptr;
 
   uint8_t* atlas_s = smem;
-  uint8_t* warp_s = smem + kAtlasBytes + warp * warp_smem_bytes(G);
+  uint8_t* warp_s = smem + kAtlasBytes + kLutBytes + warp * warp_smem_bytes(G);
   uint8_t* kinds_s = warp_s;                       // [G][kKindStride]
   uint8_t* sym_s = warp_s + G * kKindStride;       // [G][147] contiguous, same layout as the output rows
 
@@ -47,15 +47,22 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const EnvParams p, const 
     int4* dst = reinterpret_cast<int4*>(atlas_s);
     for (int i = threadIdx.x; i < kAtlasBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
+  // blit map: chunk c = lane + 32*k  ->  (cell0, off0, cell1, off1); per lane in registers, or one copy in smem
+#if MERLIN_LUT_SMEM
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem + kAtlasBytes);   // [k][lane]: conflict-free
+  for (int c = threadIdx.x; c < kChunksPerLane * 32; c += blockDim.x) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
   __syncthreads();
-
-  // per-lane blit map: chunk c = lane + 32*k  ->  (cell0, off0, cell1, off1)
+#define MERLIN_LUT(k) lut[(k) * 32 + lane]
+#else
+  __syncthreads();
   uint32_t lut[kChunksPerLane];
 #pragma unroll
   for (int k = 0; k < kChunksPerLane; ++k) {
     const int c = lane + 32 * k;
     lut[k] = c < kChunks ? chunk_lut(c) : 0u;
   }
+#define MERLIN_LUT(k) lut[k]
+#endif
 
   const int n_actions = (p.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3;
   const bool mutable_grid = p.cells != nullptr;
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) env_kernel(const EnvParams p, const 
         for (int k = 0; k < kChunksPerLane; ++k) {
           const int c = lane + 32 * k;
           if (c < kChunks) {
-            const uint32_t q = lut[k];
+            const uint32_t q = MERLIN_LUT(k);
             const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
             const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
             const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];

@@ -8,7 +8,16 @@
 
 namespace merlin {
 
-constexpr int kThreads = 256;                 // 8 warps per CTA
+#ifndef MERLIN_THREADS
+#define MERLIN_THREADS 256
+#endif
+#ifndef MERLIN_MIN_BLOCKS
+#define MERLIN_MIN_BLOCKS 1
+#endif
+#ifndef MERLIN_LUT_SMEM
+#define MERLIN_LUT_SMEM 0
+#endif
+constexpr int kThreads = MERLIN_THREADS;      // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
 constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576
 constexpr int kKindStride = 52;               // 49 tile kinds per env, padded: odd word stride -> conflict-free lanes
@@ -17,7 +26,8 @@ constexpr int kChunksPerLane = (kChunks + 31) / 32;     // 19
 __host__ __device__ constexpr int warp_smem_bytes(int G) {
   return (G * kKindStride + G * kSymBytes + 15) & ~15;
 }
-__host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + kWarps * warp_smem_bytes(G); }
+constexpr int kLutBytes = MERLIN_LUT_SMEM ? kChunksPerLane * 32 * 4 : 0;   // blit map shared by all warps
+__host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + kLutBytes + kWarps * warp_smem_bytes(G); }
 
 struct EnvParams {
   // geometry / behaviour

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libmerlin_b200.so")
+LIB_PATH = os.environ.get("MERLIN_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "libmerlin_b200.so")
 
 OK, EINVAL, ECUDA, ESTATE, ENOMEM = 0, -1, -2, -3, -4
 F_AUTO_RESET, F_RESET_SAME, F_SEVEN_ACTIONS, F_STUCK_PENALTY, F_EXPLORE_BONUS = 0x1, 0x2, 0x4, 0x8, 0x10

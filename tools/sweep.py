@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--grid", type=int, default=16)
     ap.add_argument("--difficulty", default="mediumhard")
+    ap.add_argument("--modes", default="rgb,symbolic")
+    ap.add_argument("--compact", action="store_true")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
@@ -43,7 +45,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     for N in [int(x) for x in a.sizes.split(",")]:
-        for mode in ("rgb", "symbolic"):
+        for mode in a.modes.split(","):
             rgb = mode == "rgb"
             algo = (56 * 56 * 3 if rgb else 147) + S * S + 32 + 8 + 6
             env = BatchedMerlinEnv(N, cells, agent, width=S, height=S, device=dev, want_rgb=rgb, want_symbolic=not rgb)
@@ -76,7 +78,11 @@ def main():
                    "ms_per_launch_l2_flushed_median": ms_cold, "achieved_gbs_l2_flushed": algo * N / ms_cold / 1e6,
                    "working_set_mb": algo * N / 1e6}
             rows.append(row)
-            print(json.dumps(row), flush=True)
+            if a.compact:
+                print(f"N={N:8d} {mode:8s} b2b {ms_b2b*1e3:8.1f} us  {row['env_steps_per_s']:.3e}/s  frac {row['frac_of_hbm_peak']:.3f}  "
+                      f"cold {ms_cold*1e3:8.1f} us", flush=True)
+            else:
+                print(json.dumps(row), flush=True)
             env.close()
             del env, acts
     out = {"what": f"{a.difficulty} {S}x{S} step+gen_obs sweep on 1 GPU", "hbm_peak_gbs": peak, "steps": a.steps,
