@@ -210,12 +210,12 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(envs):
+def ncu_traffic(envs, kernel=None):
     """DRAM bytes per launch of the step kernel from the committed ncu --set full capture, if it matches."""
     try:
         with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
             t = json.load(f)
-        if int(t.get("envs", -1)) == envs:
+        if int(t.get("envs", -1)) == envs and (kernel is None or t.get("kernel") == kernel):
             return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
     except (OSError, KeyError, ValueError):
         pass
@@ -278,26 +278,66 @@ def run_ours(args):
         h_ring = 8
         h_act = torch.randint(0, 3, (h_ring, N), dtype=torch.int64).pin_memory()
         d_act = torch.empty(N, dtype=torch.int64, device=dev)
-        h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
-        h_te = torch.empty(N, dtype=torch.bool).pin_memory()
-        h_tr = torch.empty(N, dtype=torch.bool).pin_memory()
+        # Two steps in flight: the H2D copy of step i+1's actions and the D2H copy of step i-1's results run on their
+        # own streams beside step i's kernel; the host blocks on step i-1's results before it submits step i+1, so
+        # every step's reward/flags are owned by the host one step later (what an asynchronous actor loop does).
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        d_act2 = [torch.empty(N, dtype=torch.int64, device=dev) for _ in range(2)]
+        bufs = [env.make_step_buffers() for _ in range(2)]
+        h_out = [(torch.empty(N, dtype=torch.float32).pin_memory(), torch.empty(N, dtype=torch.bool).pin_memory(),
+                  torch.empty(N, dtype=torch.bool).pin_memory()) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_k = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step(i, h_obs=None):
+        def e2e_run(n):
+            for b in range(2):
+                ev_k[b].record(main)
+                ev_out[b].record(s_out)
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_k[b])              # step i-2 has consumed this action buffer
+                    d_act2[b].copy_(h_act[i % h_ring], non_blocking=True)
+                    ev_in[b].record(s_in)
+                main.wait_event(ev_in[b])
+                main.wait_event(ev_out[b])                # step i-2's results have left this output buffer
+                env.step(d_act2[b], out=bufs[b])
+                ev_k[b].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_k[b])
+                    h_out[b][0].copy_(bufs[b].reward, non_blocking=True)
+                    h_out[b][1].copy_(bufs[b].terminated, non_blocking=True)
+                    h_out[b][2].copy_(bufs[b].truncated, non_blocking=True)
+                    ev_out[b].record(s_out)
+                if i > 0:
+                    ev_out[1 - b].synchronize()           # host now owns step i-1's reward / flags
+            ev_out[(n - 1) & 1].synchronize()
+
+        e2e_run(4)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(Ke)
+        barrier()
+        dt = time.perf_counter() - t0
+        # serial variant (copy in, step, copy out, synchronise -- one step at a time)
+        h_rew, h_te, h_tr = h_out[0]
+
+        def e2e_step(i):
             d_act.copy_(h_act[i % h_ring], non_blocking=True)
             obs, r, te, tr, _ = env.step(d_act)
             h_rew.copy_(r, non_blocking=True); h_te.copy_(te, non_blocking=True); h_tr.copy_(tr, non_blocking=True)
-            if h_obs is not None:
-                h_obs.copy_(obs, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller owns the results on the host now
+            torch.cuda.current_stream().synchronize()
 
         for i in range(3):
             e2e_step(i)
         barrier()
-        t0 = time.perf_counter()
+        t2 = time.perf_counter()
         for i in range(Ke):
             e2e_step(i)
         barrier()
-        dt = time.perf_counter() - t0
+        dt_serial = time.perf_counter() - t2
         # variant with every observation copied to the host as well (what a host-side consumer would need)
         Ko = min(K, 4)
         n_host = min(N, 1 << 17)  # bound pinned memory: copy the first 131072 frames (1.2 GB) and scale
@@ -313,14 +353,14 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
         barrier()
         dt_obs = time.perf_counter() - t1
-        e2e = {"seconds": dt, "steps": Ke, "seconds_obs": dt_obs, "steps_obs": Ko}
+        e2e = {"seconds": dt, "steps": Ke, "seconds_obs": dt_obs, "steps_obs": Ko, "seconds_serial": dt_serial}
 
     # ---- reduce over ranks: max time, rank 0 prints -----------------------------------------------------------
-    times = torch.tensor([ms, e2e["seconds"] if e2e else 0.0, e2e["seconds_obs"] if e2e else 0.0], device=dev,
-                         dtype=torch.float64)
+    times = torch.tensor([ms, e2e["seconds"] if e2e else 0.0, e2e["seconds_obs"] if e2e else 0.0,
+                          e2e["seconds_serial"] if e2e else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_s, e2e_obs_s = [float(x) for x in times.tolist()]
+    ms_max, e2e_s, e2e_obs_s, e2e_serial_s = [float(x) for x in times.tolist()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,7 +384,7 @@ def run_ours(args):
         "clocks": clocks,
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(N), "peak_source": peak_src, "kernel": "merlin::env_kernel<32,true>",
+                     "traffic": ncu_traffic(N, env.step_kernel()), "peak_source": peak_src, "kernel": env.step_kernel(),
                      "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "env_steps_per_launch": N,
                      "launch_ms": kernel_ms},
     }
@@ -353,6 +393,9 @@ def run_ours(args):
         d2h = N * (4 + 1 + 1)
         line["e2e"] = {"value": world * N * e2e["steps"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "obs_resident_in_hbm": True, "steps": e2e["steps"],
+                       "pipelining": "two steps in flight (copies on side streams); host owns step i's results before "
+                                     "submitting step i+2",
+                       "value_serial": world * N * e2e["steps"] / e2e_serial_s,
                        "value_obs_to_host": world * N * e2e["steps_obs"] / e2e_obs_s,
                        "d2h_bytes_per_step_obs_to_host": N * (56 * 56 * 3 + 4)}
     if not args.skip_cpu_baseline:

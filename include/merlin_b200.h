@@ -108,6 +108,11 @@ int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state_xyds /* int4[N]: pose
 int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float* episode_return);
 int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count); /* synchronises the device */
 int64_t merlin_env_launch_count(merlin_env_t* h);             /* kernels launched so far by this handle */
+/* Tuning/testing knob, process-wide: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
+ * 3 = CTA-tile kernel.  All kernels produce identical results. */
+int merlin_set_kernel_choice(int choice);
+/* Name of the kernel merlin_env_step launches for this handle (rgb != 0: with an RGB observation). */
+const char* merlin_env_step_kernel(merlin_env_t* h, int rgb);
 
 /* GAE + returns over a time-major [T][N] rollout (all DEVICE f32). done = terminated|truncated as 0/1.
  * adv[t] = delta_t + gamma*lam*(1-done_t)*adv[t+1]; ret = val + adv.  fp32, unfused, reference op order. */

@@ -59,6 +59,8 @@ struct merlin_env {
   uint8_t* pool_cells = nullptr;
   uint32_t* pool_agent = nullptr;
   uint8_t* atlas = nullptr;
+  uint32_t* blit_lut = nullptr;
+  uint32_t tile_present[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
   unsigned long long* bad_actions = nullptr;
 };
 
@@ -70,6 +72,8 @@ static EnvParams base_params(const merlin_env* h) {
   p.stuck_penalty = h->cfg.stuck_penalty; p.explore_bonus = h->cfg.explore_bonus;
   p.state = h->state; p.ep_return = h->ep_return; p.cells = h->cells; p.visited = h->visited;
   p.pool_cells = h->pool_cells; p.pool_agent = h->pool_agent; p.atlas = h->atlas; p.bad_actions = h->bad_actions;
+  p.blit_lut = h->blit_lut;
+  for (int i = 0; i < 4; ++i) p.tile_present[i] = h->tile_present[i];
   return p;
 }
 
@@ -118,6 +122,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   ok = ok && cudaMalloc(&h->ep_return, N * sizeof(float)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   if (ok && h->mutable_grid) ok = cudaMalloc(&h->cells, N * h->cell_stride) == cudaSuccess;
   if (ok && (cfg->flags & MERLIN_F_EXPLORE_BONUS)) ok = cudaMalloc(&h->visited, N * h->vis_words * sizeof(uint32_t)) == cudaSuccess;
   if (!ok) {
@@ -129,6 +134,11 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   cudaMemset(h->ep_return, 0, N * sizeof(float));
   cudaMemset(h->bad_actions, 0, sizeof(unsigned long long));
   cudaMemset(h->atlas, 0, kAtlasBytes);
+  {
+    uint32_t lut[kChunksPerLane * 32];
+    for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
+    cudaMemcpy(h->blit_lut, lut, sizeof lut, cudaMemcpyHostToDevice);
+  }
   if (h->cells) cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride);
   if (h->visited) cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t));
   if ((err = cudaDeviceSynchronize()) != cudaSuccess) { merlin_env_destroy(h); return cuda_fail(err, "init"); }
@@ -141,6 +151,7 @@ int merlin_env_destroy(merlin_env_t* h) {
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
   cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
+  cudaFree(h->blit_lut);
   delete h;
   return MERLIN_OK;
 }
@@ -150,6 +161,8 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
   const int W = h->cfg.width, H = h->cfg.height, HW = W * H;
   std::vector<uint8_t> packed((size_t)n_layouts * h->cell_stride, (uint8_t)CODE_EMPTY);
   std::vector<uint32_t> agent((size_t)n_layouts);
+  // atlas slots a frame of this pool can show: the invisible tile, highlighted empty, the agent, every code present
+  uint32_t present[4] = {(1u << KIND_UNSEEN) | (1u << CODE_EMPTY) | (1u << KIND_AGENT), 0, 0, 0};
   for (int l = 0; l < n_layouts; ++l) {
     for (int k = 0; k < HW; ++k) {
       const uint8_t c = cells[(size_t)l * HW + k];
@@ -161,6 +174,7 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
         return fail(MERLIN_EINVAL, msg);
       }
       packed[(size_t)l * h->cell_stride + k] = c;
+      present[c >> 5] |= 1u << (c & 31);
     }
     const int x = agent_xyd[3 * l], y = agent_xyd[3 * l + 1], d = agent_xyd[3 * l + 2];
     if (x < 0 || x >= W || y < 0 || y >= H || d < 0 || d > 3) return fail(MERLIN_EINVAL, "agent pose outside the grid");
@@ -181,6 +195,8 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
   cudaDeviceSynchronize();  // nothing may still be reading the old pool
   cudaFree(h->pool_cells); cudaFree(h->pool_agent);
   h->pool_cells = d_cells; h->pool_agent = d_agent; h->n_layouts = n_layouts;
+  // pickup/drop/toggle create codes the pool does not hold (door states, carried objects): stage the whole atlas then
+  for (int i = 0; i < 4; ++i) h->tile_present[i] = h->mutable_grid ? 0xffffffffu : present[i];
   h->was_reset = false;
   return merlin_env_set_cursors(h, nullptr);
 }
@@ -281,6 +297,16 @@ int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count) {
 }
 
 int64_t merlin_env_launch_count(merlin_env_t* h) { return h ? h->launches : 0; }
+
+const char* merlin_env_step_kernel(merlin_env_t* h, int rgb) {
+  return h ? step_kernel_name(h->cfg.n_envs, rgb != 0, h->sm_count) : "";
+}
+
+int merlin_set_kernel_choice(int choice) {
+  if (choice < 0 || choice > 3) return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp) or 3 (tile)");
+  set_kernel_choice(choice);
+  return MERLIN_OK;
+}
 
 int merlin_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv, float* ret,
                int32_t T, int32_t N, double gamma, double lam, void* stream) {

@@ -1,21 +1,24 @@
 // env_kernels.cu -- fused MERLIN env kernels for sm_100a.
 //
-//   env_kernel<G, STEP=true >  : step + wrappers + auto-reset + gen_obs(+process_vis) + symbolic encode + RGB blit
-//   env_kernel<G, STEP=false>  : (masked) reset + the same observation path
+// Every kernel does the same work per environment -- step + wrappers + auto-reset (STEP = true) or a masked reset
+// (STEP = false), then gen_obs (+process_vis), the symbolic encode and the RGB frame -- and differs only in how
+// environments are mapped onto the machine.  Two phases:
 //
-// Mapping (HBM-bound streaming writer; tensor cores are not involved):
-//   * one WARP owns G consecutive environments (G = 32 at scale; smaller G only to spread tiny batches
-//     over more SMs).  Phase A runs one env per lane: 128-bit coalesced load of the packed state,
-//     coalesced action read, step logic, reward shaping, 49-cell window gather, bitmask visibility.
-//     The 49 tile kinds (and the 147 symbolic bytes) of each env go to shared memory.
-//   * Phase B: the warp walks its G envs; per env the 32 lanes emit the 9408-byte frame as 588
-//     coalesced 16-byte streaming stores, each assembled from two 8-byte reads of the tile atlas
-//     held in shared memory.  Per-lane chunk->(cell, tile offset) maps are computed once per kernel
-//     and live in registers.
-//   * All per-env scalars (reward, flags, episode stats, state) are written by lane=env, i.e. coalesced.
-//   * Finished envs are restarted by the whole warp (coalesced 16-byte copies of the pool layout) when the
-//     grid is mutable; with the 3-action set grids are immutable and envs read the pool in place.
+//   state phase   step logic, reward shaping, restart, 49-cell window gather, bitmask visibility -> the 49 tile
+//                 kinds (and 147 symbolic bytes) of the env, in shared memory.  ~20 warp-instructions per env when
+//                 run one env per LANE (state_phase<G>), ~250 when one WARP serves one env cooperatively.
+//   frame phase   the 9408-byte frame as 588 coalesced 16-byte streaming stores per env, each assembled from two
+//                 8-byte reads of the tile atlas in shared memory (blit_frame); always one warp per env.
 //
+//   env_kernel<G>        a warp owns G consecutive envs for both phases (G = 32 at scale).  Cheapest in instructions;
+//                        the unit of work is G frames (300 KB at G = 32), so it wants many groups per warp.
+//   env_kernel_tile<T>   a CTA owns a tile of T envs: warp 0 runs the state phase one env per lane, then ALL warps
+//                        of the CTA share the T frames.  Same cheap state phase, 8x finer frame-phase granularity:
+//                        fills the SMs from a few thousand envs up and has no tail at a few tiles per CTA.
+//   env_kernel_warp      one warp per env, cooperative state phase (two window cells per lane, warp ballots for the
+//                        transparency mask).  Lowest latency for batches too small to give each SM a tile.
+//
+// HBM-bound streaming writers; tensor cores are not involved (there is no contraction on this path).
 // Algorithmic HBM bytes per env-step (16x16, RGB): 9408 obs + 256 grid + 32 state + 8 action + 6 = 9710.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,212 +32,225 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int G, bool STEP>
-__global__ void __launch_bounds__(kThreads, MERLIN_MIN_BLOCKS) env_kernel(const EnvParams p, const int n_groups) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const bool want_rgb = p.obs_rgb != nullptr;
-  const bool want_sym = p.obs_sym != nullptr;
+struct Flags {
+  int n_actions;
+  bool mutable_grid, stuck_on, explore_on, auto_reset, advance, want_rgb, want_sym;
+  __device__ __forceinline__ explicit Flags(const EnvParams& p)
+      : n_actions((p.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3), mutable_grid(p.cells != nullptr),
+        stuck_on(p.flags & MERLIN_F_STUCK_PENALTY), explore_on(p.flags & MERLIN_F_EXPLORE_BONUS),
+        auto_reset(p.flags & MERLIN_F_AUTO_RESET), advance(!(p.flags & MERLIN_F_RESET_SAME)),
+        want_rgb(p.obs_rgb != nullptr), want_sym(p.obs_sym != nullptr) {}
+};
 
-  uint8_t* atlas_s = smem;
-  uint8_t* warp_s = smem + kAtlasBytes + kLutBytes + warp * warp_smem_bytes(G);
-  uint8_t* kinds_s = warp_s;                       // [G][kKindStride]
-  uint8_t* sym_s = warp_s + G * kKindStride;       // [G][147] contiguous, same layout as the output rows
-
-  if (want_rgb) {  // stage the 24 KB tile atlas once per CTA
-    const int4* src = reinterpret_cast<const int4*>(p.atlas);
-    int4* dst = reinterpret_cast<int4*>(atlas_s);
-    for (int i = threadIdx.x; i < kAtlasBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+// Stage the tile atlas: only the slots a frame of this handle's layout pool can show (5 of 128 for the MERLIN
+// scenarios: 960 B instead of 24 KB), at their usual offsets.  All threads of the CTA take part.
+__device__ __forceinline__ void stage_atlas(const EnvParams& p, uint8_t* atlas_s) {
+  const int4* src = reinterpret_cast<const int4*>(p.atlas);
+  int4* dst = reinterpret_cast<int4*>(atlas_s);
+  for (int i = threadIdx.x; i < kAtlasBytes / 16; i += blockDim.x) {
+    const int tile = i / (kTileBytes / 16);
+    if ((p.tile_present[tile >> 5] >> (tile & 31)) & 1u) dst[i] = __ldg(src + i);
   }
-  // blit map: chunk c = lane + 32*k  ->  (cell0, off0, cell1, off1); per lane in registers, or one copy in smem
-#if MERLIN_LUT_SMEM
-  uint32_t* lut = reinterpret_cast<uint32_t*>(smem + kAtlasBytes);   // [k][lane]: conflict-free
-  for (int c = threadIdx.x; c < kChunksPerLane * 32; c += blockDim.x) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
-  __syncthreads();
-#define MERLIN_LUT(k) lut[(k) * 32 + lane]
-#else
-  __syncthreads();
-  uint32_t lut[kChunksPerLane];
+}
+
+// Per-lane blit map: chunk c = lane + 32*k -> (cell0, off0, cell1, off1), from the table built at handle creation.
+__device__ __forceinline__ void load_lut(const EnvParams& p, int lane, uint32_t (&lut)[kChunksPerLane]) {
+#pragma unroll
+  for (int k = 0; k < kChunksPerLane; ++k) lut[k] = __ldg(p.blit_lut + k * 32 + lane);
+}
+
+// Frame phase for one env: `kp` = its 49 tile kinds in shared memory.
+__device__ __forceinline__ void blit_frame(const uint8_t* atlas_s, const uint8_t* kp, const uint32_t (&lut)[kChunksPerLane],
+                                           uint8_t* frame, int lane) {
+  const uint2* atlas64 = reinterpret_cast<const uint2*>(atlas_s);
 #pragma unroll
   for (int k = 0; k < kChunksPerLane; ++k) {
     const int c = lane + 32 * k;
-    lut[k] = c < kChunks ? chunk_lut(c) : 0u;
+    if (c < kChunks) {
+      const uint32_t q = lut[k];
+      const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
+      const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
+      const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];
+      st_stream_v4(frame + c * 16, a.x, a.y, b.x, b.y);
+    }
   }
-#define MERLIN_LUT(k) lut[k]
-#endif
+}
 
-  const int n_actions = (p.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3;
-  const bool mutable_grid = p.cells != nullptr;
-  const bool stuck_on = p.flags & MERLIN_F_STUCK_PENALTY;
-  const bool explore_on = p.flags & MERLIN_F_EXPLORE_BONUS;
-  const bool auto_reset = p.flags & MERLIN_F_AUTO_RESET;
-  const bool advance = !(p.flags & MERLIN_F_RESET_SAME);
+// Symbolic rows of `n_here` consecutive envs from shared memory (same layout as the output), by `nthreads` threads.
+__device__ __forceinline__ void emit_sym_rows(uint8_t* out, const uint8_t* sym_s, int n_here, unsigned render_mask,
+                                              int tid, int nthreads) {
+  const unsigned full = n_here >= 32 ? 0xffffffffu : ((1u << n_here) - 1u);
+  if (render_mask == full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (n_here * kSymBytes) % 16 == 0) {
+    const int4* src = reinterpret_cast<const int4*>(sym_s);
+    int4* dst = reinterpret_cast<int4*>(out);
+    for (int i = tid; i < n_here * kSymBytes / 16; i += nthreads) dst[i] = src[i];
+  } else {
+    for (int b = tid; b < n_here * kSymBytes; b += nthreads) {
+      const int i = b / kSymBytes;
+      if ((render_mask >> i) & 1) out[b] = sym_s[b];
+    }
+  }
+}
+
+// State phase, one env per lane, for the G envs e0 .. e0+G-1 (lanes >= G idle).  Must be called by a full warp.
+// Leaves kinds_s[lane][kKindStride] / sym_s[lane][147] filled for the envs whose bit is set in the returned mask.
+template <int G, bool STEP>
+__device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags& f, int e0, int lane, uint8_t* kinds_s,
+                                                uint8_t* sym_s) {
+  const int e = e0 + lane;
+  const bool active = lane < G && e < p.N;
+  EnvState s{};
+  bool restart = false;   // this lane's env (re)loads a layout now
+  bool render = active;   // this lane's env gets its observation written
+  if (active) {
+    const int4 st = p.state[e];
+    unpack_state(st.x, st.y, st.z, st.w, s);
+  }
+  float ep_ret = active ? p.ep_return[e] : 0.f;
+
+  if (STEP) {
+    if (active) {
+      const uint8_t* grid = f.mutable_grid ? p.cells + (size_t)e * p.cell_stride
+                                           : p.pool_cells + (size_t)s.layout * p.cell_stride;
+      const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
+      const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
+      const int fidx = fy * p.W + fx;
+      const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
+      StepResult r = step_logic(s, p.actions[e], f.n_actions, fwd, inb, fidx, p.max_steps);
+      if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
+      if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
+
+      uint32_t vword = 0;
+      const int cell = s.y * p.W + s.x;
+      uint32_t* vptr = nullptr;
+      if (f.explore_on) { vptr = p.visited + (size_t)e * p.vis_words + (cell >> 5); vword = *vptr; }
+      bool stuck = false;
+      const uint32_t vword_in = vword;
+      const double rew_d = shape_reward(s, r.reward, f.stuck_on, p.stuck_max_stay, p.stuck_penalty, f.explore_on,
+                                        p.explore_bonus, vword, cell & 31, stuck);
+      if (f.explore_on && vword != vword_in) *vptr = vword;
+      const float rew = (float)rew_d;
+      ep_ret += rew;
+      const bool done = r.terminated || r.truncated;
+      p.reward[e] = rew;
+      p.terminated[e] = r.terminated ? 1 : 0;
+      p.truncated[e] = r.truncated ? 1 : 0;
+      if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
+      if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
+      if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
+      restart = done && f.auto_reset;
+    }
+  } else {
+    restart = active && (p.reset_mask == nullptr || p.reset_mask[e] != 0);
+    render = restart;
+  }
+
+  // (re)start: pose from the pool, counters cleared, cursor advanced; mutable grids / visited maps are
+  // re-initialised by the whole warp with coalesced copies
+  const unsigned restart_mask = __ballot_sync(0xffffffffu, restart);
+  if (restart_mask) {
+    // pool index this env loads: pending first layout, else the next (PPO) or the same (FOMAML) one
+    const int load_cur = s.layout < 0 ? ~s.layout
+                                      : (f.advance ? (int)(((long long)s.layout + p.N) % p.n_layouts) : s.layout);
+    if (restart) {
+      const uint32_t a = p.pool_agent[load_cur];
+      s.x = a & 0xff; s.y = (a >> 8) & 0xff; s.dir = (a >> 16) & 3; s.carry = 0;
+      s.step_count = 0; s.stay = 0; s.last_x = s.x; s.last_y = s.y;
+      ep_ret = 0.f;
+    }
+    if (f.mutable_grid || f.explore_on) {
+      unsigned m = restart_mask;
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int cur = __shfl_sync(0xffffffffu, load_cur, src);
+        const int sx = __shfl_sync(0xffffffffu, s.x, src), sy = __shfl_sync(0xffffffffu, s.y, src);
+        const size_t ee = (size_t)(e0 + src);
+        if (f.mutable_grid) {
+          const int4* from = reinterpret_cast<const int4*>(p.pool_cells + (size_t)cur * p.cell_stride);
+          int4* to = reinterpret_cast<int4*>(p.cells + ee * p.cell_stride);
+          for (int i = lane; i < p.cell_stride / 16; i += 32) to[i] = from[i];
+        }
+        if (f.explore_on) {
+          const int cell = sy * p.W + sx;
+          for (int i = lane; i < p.vis_words; i += 32)
+            p.visited[ee * p.vis_words + i] = (i == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
+        }
+      }
+      __syncwarp();
+    }
+    if (restart) s.layout = load_cur;
+  }
+
+  if (active && (STEP || restart)) {
+    int4 st;
+    pack_state(s, st.x, st.y, st.z, st.w);
+    p.state[e] = st;
+    p.ep_return[e] = ep_ret;
+  }
+
+  // observation, part 1 (per lane): window gather -> visibility -> tile kinds (+ symbolic bytes) in smem
+  if ((f.want_rgb || f.want_sym) && render) {
+    const uint8_t* grid = f.mutable_grid ? p.cells + (size_t)e * p.cell_stride
+                                         : p.pool_cells + (size_t)s.layout * p.cell_stride;
+    uint8_t* kind = kinds_s + lane * kKindStride;
+    const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
+    const uint64_t vis = visibility(transp);
+    uint8_t* sym = sym_s + lane * kSymBytes;
+#pragma unroll
+    for (int vi = 0; vi < kView; ++vi) {
+#pragma unroll
+      for (int vj = 0; vj < kView; ++vj) {
+        const int c = vi * kView + vj;
+        const bool seen = (vis >> (vj * kView + vi)) & 1;
+        uint32_t code = kind[c];
+        const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
+        if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
+        kind[c] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
+        if (f.want_sym) {
+          uint8_t t = 0, col = 0, stt = 0;
+          if (seen) sym_of_code(code, t, col, stt);
+          sym[c * 3 + 0] = t; sym[c * 3 + 1] = col; sym[c * 3 + 2] = stt;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  return __ballot_sync(0xffffffffu, render);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// env_kernel<G, STEP>: a warp owns G consecutive envs.
+template <int G, bool STEP>
+__global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, const int n_groups) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const Flags f(p);
+  uint8_t* atlas_s = smem;
+  uint8_t* warp_s = smem + kAtlasBytes + warp * warp_smem_bytes(G);
+  uint8_t* kinds_s = warp_s;                       // [G][kKindStride]
+  uint8_t* sym_s = warp_s + G * kKindStride;       // [G][147] contiguous, same layout as the output rows
+
+  uint32_t lut[kChunksPerLane];
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    load_lut(p, lane, lut);
+  }
+  __syncthreads();
+
   const int warps_per_cta = blockDim.x >> 5;
-
   for (int g = blockIdx.x * warps_per_cta + warp; g < n_groups; g += gridDim.x * warps_per_cta) {
     const int e0 = g * G;
-    const int e = e0 + lane;
-    const bool active = lane < G && e < p.N;
-
-    // ------------------------------------------------------------------ phase A: one env per lane
-    EnvState s{};
-    bool restart = false;   // this lane's env (re)loads a layout now
-    bool render = active;   // this lane's env gets its observation written
-    if (active) {
-      const int4 st = p.state[e];
-      unpack_state(st.x, st.y, st.z, st.w, s);
-    }
-    float ep_ret = active ? p.ep_return[e] : 0.f;
-
-    if (STEP) {
-      if (active) {
-        const uint8_t* grid = mutable_grid ? p.cells + (size_t)e * p.cell_stride
-                                           : p.pool_cells + (size_t)s.layout * p.cell_stride;
-        const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
-        const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
-        const int fidx = fy * p.W + fx;
-        const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
-        StepResult r = step_logic(s, p.actions[e], n_actions, fwd, inb, fidx, p.max_steps);
-        if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
-        if (r.write_idx >= 0 && mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
-
-        uint32_t vword = 0;
-        const int cell = s.y * p.W + s.x;
-        uint32_t* vptr = nullptr;
-        if (explore_on) { vptr = p.visited + (size_t)e * p.vis_words + (cell >> 5); vword = *vptr; }
-        bool stuck = false;
-        const uint32_t vword_in = vword;
-        const double rew_d = shape_reward(s, r.reward, stuck_on, p.stuck_max_stay, p.stuck_penalty, explore_on,
-                                          p.explore_bonus, vword, cell & 31, stuck);
-        if (explore_on && vword != vword_in) *vptr = vword;
-        const float rew = (float)rew_d;
-        ep_ret += rew;
-        const bool done = r.terminated || r.truncated;
-        p.reward[e] = rew;
-        p.terminated[e] = r.terminated ? 1 : 0;
-        p.truncated[e] = r.truncated ? 1 : 0;
-        if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
-        if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
-        if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
-        restart = done && auto_reset;
-      }
-    } else {
-      restart = active && (p.reset_mask == nullptr || p.reset_mask[e] != 0);
-      render = restart;
-    }
-
-    // (re)start: pose from the pool, counters cleared, cursor advanced; mutable grids / visited maps are
-    // re-initialised by the whole warp with coalesced copies
-    const unsigned restart_mask = __ballot_sync(0xffffffffu, restart);
-    if (restart_mask) {
-      // pool index this env loads: pending first layout, else the next (PPO) or the same (FOMAML) one
-      const int load_cur = s.layout < 0 ? ~s.layout
-                                        : (advance ? (int)(((long long)s.layout + p.N) % p.n_layouts) : s.layout);
-      if (restart) {
-        const uint32_t a = p.pool_agent[load_cur];
-        s.x = a & 0xff; s.y = (a >> 8) & 0xff; s.dir = (a >> 16) & 3; s.carry = 0;
-        s.step_count = 0; s.stay = 0; s.last_x = s.x; s.last_y = s.y;
-        ep_ret = 0.f;
-      }
-      if (mutable_grid || explore_on) {
-        unsigned m = restart_mask;
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int cur = __shfl_sync(0xffffffffu, load_cur, src);
-          const int sx = __shfl_sync(0xffffffffu, s.x, src), sy = __shfl_sync(0xffffffffu, s.y, src);
-          const size_t ee = (size_t)(e0 + src);
-          if (mutable_grid) {
-            const int4* from = reinterpret_cast<const int4*>(p.pool_cells + (size_t)cur * p.cell_stride);
-            int4* to = reinterpret_cast<int4*>(p.cells + ee * p.cell_stride);
-            for (int i = lane; i < p.cell_stride / 16; i += 32) to[i] = from[i];
-          }
-          if (explore_on) {
-            const int cell = sy * p.W + sx;
-            for (int i = lane; i < p.vis_words; i += 32)
-              p.visited[ee * p.vis_words + i] = (i == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
-          }
-        }
-        __syncwarp();
-      }
-      if (restart) s.layout = load_cur;
-    }
-
-    if (active && (STEP || restart)) {
-      int4 st;
-      pack_state(s, st.x, st.y, st.z, st.w);
-      p.state[e] = st;
-      p.ep_return[e] = ep_ret;
-    }
-
-    // observation, part 1 (per lane): window gather -> visibility -> tile kinds (+ symbolic bytes) in smem
-    if ((want_rgb || want_sym) && render) {
-      const uint8_t* grid = mutable_grid ? p.cells + (size_t)e * p.cell_stride
-                                         : p.pool_cells + (size_t)s.layout * p.cell_stride;
-      uint8_t* kind = kinds_s + lane * kKindStride;
-      const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
-      const uint64_t vis = visibility(transp);
-      uint8_t* sym = sym_s + lane * kSymBytes;
-#pragma unroll
-      for (int vi = 0; vi < kView; ++vi) {
-#pragma unroll
-        for (int vj = 0; vj < kView; ++vj) {
-          const int c = vi * kView + vj;
-          const bool seen = (vis >> (vj * kView + vi)) & 1;
-          uint32_t code = kind[c];
-          const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
-          if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
-          kind[c] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
-          if (want_sym) {
-            uint8_t t = 0, col = 0, stt = 0;
-            if (seen) sym_of_code(code, t, col, stt);
-            sym[c * 3 + 0] = t; sym[c * 3 + 1] = col; sym[c * 3 + 2] = stt;
-          }
-        }
-      }
-    }
-    __syncwarp();
-
-    const unsigned render_mask = __ballot_sync(0xffffffffu, render);
-
-    // observation, part 2 (whole warp): symbolic rows out, coalesced
-    if (want_sym && render_mask) {
-      const int n_here = min(G, p.N - e0);
-      uint8_t* out = p.obs_sym + (size_t)e0 * kSymBytes;
-      const unsigned full = n_here >= 32 ? 0xffffffffu : ((1u << n_here) - 1u);
-      if (render_mask == full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (n_here * kSymBytes) % 16 == 0) {
-        const int4* src = reinterpret_cast<const int4*>(sym_s);
-        int4* dst = reinterpret_cast<int4*>(out);
-        for (int i = lane; i < n_here * kSymBytes / 16; i += 32) dst[i] = src[i];
-      } else {
-        for (int i = 0; i < n_here; ++i) {
-          if (!((render_mask >> i) & 1)) continue;
-          for (int b = lane; b < kSymBytes; b += 32) out[i * kSymBytes + b] = sym_s[i * kSymBytes + b];
-        }
-      }
-    }
-
-    // observation, part 3 (whole warp): RGB frames, 588 x 16-byte streaming stores per env
-    if (want_rgb && render_mask) {
-      const uint2* atlas64 = reinterpret_cast<const uint2*>(atlas_s);
+    const unsigned render_mask = state_phase<G, STEP>(p, f, e0, lane, kinds_s, sym_s);
+    if (f.want_sym && render_mask)
+      emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(G, p.N - e0), render_mask, lane, 32);
+    if (f.want_rgb) {
       unsigned m = render_mask;
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1;
-        const uint8_t* kp = kinds_s + i * kKindStride;
-        uint8_t* frame = p.obs_rgb + (size_t)(e0 + i) * kImgBytes;
-#pragma unroll
-        for (int k = 0; k < kChunksPerLane; ++k) {
-          const int c = lane + 32 * k;
-          if (c < kChunks) {
-            const uint32_t q = MERLIN_LUT(k);
-            const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
-            const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
-            const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];
-            st_stream_v4(frame + c * 16, a.x, a.y, b.x, b.y);
-          }
-        }
+        blit_frame(atlas_s, kinds_s + i * kKindStride, lut, p.obs_rgb + (size_t)(e0 + i) * kImgBytes, lane);
       }
     }
     __syncwarp();  // smem rows are reused by the next group
@@ -242,40 +258,323 @@ __global__ void __launch_bounds__(kThreads, MERLIN_MIN_BLOCKS) env_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int G, bool STEP>
-static cudaError_t launch_one(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  const int n_groups = (p.N + G - 1) / G;
-  const size_t smem = cta_smem_bytes(G);
-  static bool configured_dev[64] = {};  // per template instance and device
-  static int blocks_per_sm_dev[64] = {};
+// env_kernel_tile<T, STEP>: a CTA owns a tile of T <= 32 consecutive envs; warp 0 runs the state phase, every
+// warp of the CTA takes frames of the tile.  Two CTAs per SM overlap one tile's state phase with another's frames.
+#ifndef MERLIN_TILE_THREADS
+#define MERLIN_TILE_THREADS 256
+#endif
+#ifndef MERLIN_TILE_MINB
+#define MERLIN_TILE_MINB 2
+#endif
+#ifndef MERLIN_TILE_LUT_SMEM
+#define MERLIN_TILE_LUT_SMEM 0
+#endif
+constexpr int kTileThreads = MERLIN_TILE_THREADS;
+constexpr int kTileLutBytes = MERLIN_TILE_LUT_SMEM ? kChunksPerLane * 32 * 4 : 0;
+__host__ __device__ constexpr int tile_smem_bytes(int T) {
+  return kAtlasBytes + kTileLutBytes + ((T * kKindStride + T * kSymBytes + 15) & ~15) + 16;
+}
+
+template <int T, bool STEP>
+__global__ void __launch_bounds__(kTileThreads, MERLIN_TILE_MINB) env_kernel_tile(const EnvParams p, const int n_tiles) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const Flags f(p);
+  uint8_t* atlas_s = smem;
+  uint8_t* kinds_s = smem + kAtlasBytes + kTileLutBytes;   // [T][kKindStride]
+  uint8_t* sym_s = kinds_s + T * kKindStride;              // [T][147]
+  unsigned* mask_s = reinterpret_cast<unsigned*>(smem + tile_smem_bytes(T) - 16);
+
+#if MERLIN_TILE_LUT_SMEM
+  uint32_t* lut_s = reinterpret_cast<uint32_t*>(smem + kAtlasBytes);   // [k][lane]: conflict-free
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    for (int i = threadIdx.x; i < kChunksPerLane * 32; i += blockDim.x) lut_s[i] = __ldg(p.blit_lut + i);
+  }
+#else
+  uint32_t lut[kChunksPerLane];
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    load_lut(p, lane, lut);
+  }
+#endif
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int e0 = tile * T;
+    if (warp == 0) {
+      const unsigned m = state_phase<T, STEP>(p, f, e0, lane, kinds_s, sym_s);
+      if (lane == 0) *mask_s = m;
+    }
+    __syncthreads();  // kinds / sym / mask of this tile (and, first time round, the atlas) are in shared memory
+    const unsigned render_mask = *mask_s;
+    if (f.want_sym && render_mask)
+      emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(T, p.N - e0), render_mask, threadIdx.x, blockDim.x);
+    if (f.want_rgb) {
+      for (int i = warp; i < T; i += warps_per_cta)
+        if ((render_mask >> i) & 1) {
+#if MERLIN_TILE_LUT_SMEM
+          uint32_t lut[kChunksPerLane];
+#pragma unroll
+          for (int k = 0; k < kChunksPerLane; ++k) lut[k] = lut_s[k * 32 + lane];
+#endif
+          blit_frame(atlas_s, kinds_s + i * kKindStride, lut, p.obs_rgb + (size_t)(e0 + i) * kImgBytes, lane);
+        }
+    }
+    __syncthreads();  // the tile buffers are rewritten by the next state phase
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// env_kernel_warp<STEP>: one WARP per environment.
+//   * state / action / forward cell are loaded at warp-uniform addresses (one broadcast transaction each) and the
+//     step logic runs redundantly on all lanes; lane 0 alone writes the per-env outputs and the new state.
+//   * the 49-cell window is gathered two cells per lane; transparency goes through two warp ballots into the same
+//     49-bit mask the visibility routine consumes; every lane then knows the visibility of its own cells.
+constexpr int kWarpKernelThreads = 256;
+constexpr int kWarpKindStride = 64;
+
+template <bool STEP>
+__global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const EnvParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const Flags f(p);
+  uint8_t* atlas_s = smem;
+  uint8_t* kp = smem + kAtlasBytes + warp * kWarpKindStride;   // this warp's 49 tile kinds
+
+  uint32_t lut[kChunksPerLane];
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    load_lut(p, lane, lut);
+  }
+  __syncthreads();
+
+  // this lane's two window cells, in mask order c = vj*7 + vi
+  const int c0 = lane, c1 = lane + 32;
+  const int vj0 = c0 / kView, vi0 = c0 - vj0 * kView;
+  const int vj1 = c1 < kCells ? c1 / kView : 0, vi1 = c1 < kCells ? c1 - vj1 * kView : 0;
+
+  for (int e = blockIdx.x * warps_per_cta + warp; e < p.N; e += gridDim.x * warps_per_cta) {
+    EnvState s{};
+    const int4 st = p.state[e];
+    unpack_state(st.x, st.y, st.z, st.w, s);
+    float ep_ret = p.ep_return[e];
+    bool restart = false, render = true;
+
+    if (STEP) {
+      const uint8_t* grid = f.mutable_grid ? p.cells + (size_t)e * p.cell_stride
+                                           : p.pool_cells + (size_t)s.layout * p.cell_stride;
+      const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
+      const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
+      const int fidx = fy * p.W + fx;
+      const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
+      StepResult r = step_logic(s, p.actions[e], f.n_actions, fwd, inb, fidx, p.max_steps);
+      uint32_t vword = 0;
+      const int cell = s.y * p.W + s.x;
+      uint32_t* vptr = nullptr;
+      if (f.explore_on) { vptr = p.visited + (size_t)e * p.vis_words + (cell >> 5); vword = *vptr; }
+      bool stuck = false;
+      const uint32_t vword_in = vword;
+      const double rew_d = shape_reward(s, r.reward, f.stuck_on, p.stuck_max_stay, p.stuck_penalty, f.explore_on,
+                                        p.explore_bonus, vword, cell & 31, stuck);
+      const float rew = (float)rew_d;
+      ep_ret += rew;
+      const bool done = r.terminated || r.truncated;
+      __syncwarp();  // every lane has read the old grid cell / visited word before lane 0 overwrites them
+      if (lane == 0) {
+        if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
+        if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
+        if (f.explore_on && vword != vword_in) *vptr = vword;
+        p.reward[e] = rew;
+        p.terminated[e] = r.terminated ? 1 : 0;
+        p.truncated[e] = r.truncated ? 1 : 0;
+        if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
+        if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
+        if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
+      }
+      restart = done && f.auto_reset;
+    } else {
+      restart = p.reset_mask == nullptr || p.reset_mask[e] != 0;
+      render = restart;
+    }
+
+    if (restart) {  // warp-uniform
+      const int load_cur = s.layout < 0 ? ~s.layout
+                                        : (f.advance ? (int)(((long long)s.layout + p.N) % p.n_layouts) : s.layout);
+      const uint32_t a = p.pool_agent[load_cur];
+      s.x = a & 0xff; s.y = (a >> 8) & 0xff; s.dir = (a >> 16) & 3; s.carry = 0;
+      s.step_count = 0; s.stay = 0; s.last_x = s.x; s.last_y = s.y;
+      ep_ret = 0.f;
+      s.layout = load_cur;
+      if (f.mutable_grid) {
+        __syncwarp();
+        const int4* from = reinterpret_cast<const int4*>(p.pool_cells + (size_t)load_cur * p.cell_stride);
+        int4* to = reinterpret_cast<int4*>(p.cells + (size_t)e * p.cell_stride);
+        for (int i = lane; i < p.cell_stride / 16; i += 32) to[i] = from[i];
+      }
+      if (f.explore_on) {
+        __syncwarp();
+        const int cell = s.y * p.W + s.x;
+        for (int i = lane; i < p.vis_words; i += 32)
+          p.visited[(size_t)e * p.vis_words + i] = (i == (cell >> 5)) ? (1u << (cell & 31)) : 0u;
+      }
+    }
+    if (lane == 0 && (STEP || restart)) {
+      int4 o;
+      pack_state(s, o.x, o.y, o.z, o.w);
+      p.state[e] = o;
+      p.ep_return[e] = ep_ret;
+    }
+    if (!render || !(f.want_rgb || f.want_sym)) continue;
+    __syncwarp();  // grid writes of this step (pickup/drop/toggle, restart copy) are visible to the gather below
+
+    // observation, part 1: two window cells per lane -> ballot -> visibility -> tile kinds (+ symbolic bytes)
+    const uint8_t* grid = f.mutable_grid ? p.cells + (size_t)e * p.cell_stride
+                                         : p.pool_cells + (size_t)s.layout * p.cell_stride;
+    const int fx = dir_dx(s.dir), fy = dir_dy(s.dir);
+    const int rx = -fy, ry = fx;
+    uint32_t code0, code1 = CODE_WALL;
+    {
+      const int a = (kView - 1) - vj0, b = vi0 - kView / 2;
+      const int wx = s.x + a * fx + b * rx, wy = s.y + a * fy + b * ry;
+      code0 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
+    }
+    if (c1 < kCells) {
+      const int a = (kView - 1) - vj1, b = vi1 - kView / 2;
+      const int wx = s.x + a * fx + b * rx, wy = s.y + a * fy + b * ry;
+      code1 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
+    }
+    const unsigned t0 = __ballot_sync(0xffffffffu, !((M_OPAQUE >> (code0 & 0xf)) & 1u));
+    const unsigned t1 = __ballot_sync(0xffffffffu, c1 < kCells && !((M_OPAQUE >> (code1 & 0xf)) & 1u));
+    const uint64_t vis = visibility((uint64_t)t0 | ((uint64_t)t1 << 32));
+    uint8_t* sym_out = f.want_sym ? p.obs_sym + (size_t)e * kSymBytes : nullptr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h ? c1 : c0;
+      if (c >= kCells) break;
+      const int vi = h ? vi1 : vi0, vj = h ? vj1 : vj0;
+      uint32_t code = h ? code1 : code0;
+      const bool seen = (vis >> c) & 1;
+      const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
+      if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
+      const int k = vi * kView + vj;
+      kp[k] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
+      if (f.want_sym) {
+        uint8_t t = 0, col = 0, stt = 0;
+        if (seen) sym_of_code(code, t, col, stt);
+        sym_out[k * 3 + 0] = t; sym_out[k * 3 + 1] = col; sym_out[k * 3 + 2] = stt;
+      }
+    }
+    __syncwarp();
+    if (f.want_rgb) blit_frame(atlas_s, kp, lut, p.obs_rgb + (size_t)e * kImgBytes, lane);
+    __syncwarp();  // kp is reused by this warp's next env
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers: persistent grids of (SMs x resident CTAs), capped by the work available
+template <typename Kernel>
+static cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int& blocks_per_sm) {
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem);
+  if (err != cudaSuccess) return err;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  return cudaSuccess;
+}
+
+static int current_device_slot() {
   int dev = 0;
   cudaGetDevice(&dev);
-  dev &= 63;
-  bool& configured = configured_dev[dev];
-  int& blocks_per_sm = blocks_per_sm_dev[dev];
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(env_kernel<G, STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return dev & 63;
+}
+
+template <int G, bool STEP>
+static cudaError_t launch_group_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  const int n_groups = (p.N + G - 1) / G;
+  const size_t smem = cta_smem_bytes(G);
+  static int blocks_per_sm_dev[64] = {};  // per template instance and device; 0 = not configured yet
+  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  if (!blocks_per_sm) {
+    cudaError_t err = resident_ctas(env_kernel<G, STEP>, kThreads, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<G, STEP>, kThreads, smem);
-    if (err != cudaSuccess) return err;
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    configured = true;
   }
-  const int ctas_needed = (n_groups + kWarps - 1) / kWarps;
-  int grid = sm_count * blocks_per_sm;
-  if (grid > ctas_needed) grid = ctas_needed;
+  const int grid = min(sm_count * blocks_per_sm, (n_groups + kWarps - 1) / kWarps);
   env_kernel<G, STEP><<<grid, kThreads, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
 }
 
+template <int T, bool STEP>
+static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  const int n_tiles = (p.N + T - 1) / T;
+  const size_t smem = tile_smem_bytes(T);
+  static int blocks_per_sm_dev[64] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  if (!blocks_per_sm) {
+    cudaError_t err = resident_ctas(env_kernel_tile<T, STEP>, kTileThreads, smem, blocks_per_sm);
+    if (err != cudaSuccess) return err;
+  }
+  const int grid = min(sm_count * blocks_per_sm, n_tiles);
+  env_kernel_tile<T, STEP><<<grid, kTileThreads, smem, stream>>>(p, n_tiles);
+  return cudaGetLastError();
+}
+
+template <bool STEP>
+static cudaError_t launch_warp_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  constexpr int warps = kWarpKernelThreads / 32;
+  const size_t smem = kAtlasBytes + warps * kWarpKindStride;
+  static int blocks_per_sm_dev[64] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  if (!blocks_per_sm) {
+    cudaError_t err = resident_ctas(env_kernel_warp<STEP>, kWarpKernelThreads, smem, blocks_per_sm);
+    if (err != cudaSuccess) return err;
+  }
+  const int grid = min(sm_count * blocks_per_sm, (p.N + warps - 1) / warps);
+  env_kernel_warp<STEP><<<grid, kWarpKernelThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+static int g_kernel_choice = 0;
+void set_kernel_choice(int choice) { g_kernel_choice = choice; }
+
 template <bool STEP>
 static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  int choice = g_kernel_choice;
+  if (choice == 0) {
+    // symbolic-only observations are instruction-bound: the cheapest state phase, a warp per group of envs
+    if (p.obs_rgb == nullptr) choice = 1;
+    else choice = MERLIN_AUTO_RGB_CHOICE(p.N, sm_count);
+  }
+  if (choice == 2) return launch_warp_kernel<STEP>(p, sm_count, stream);
+  if (choice == 3) {
+    // tiles of 32 envs once every SM gets a few; smaller tiles spread a small batch over more CTAs
+    if (p.N >= sm_count * 2 * 32) return launch_tile_kernel<32, STEP>(p, sm_count, stream);
+    if (p.N >= sm_count * 2 * 16) return launch_tile_kernel<16, STEP>(p, sm_count, stream);
+    return launch_tile_kernel<8, STEP>(p, sm_count, stream);
+  }
   // pick the largest group size that still yields >= ~8 warps per SM; tiny batches use smaller groups
   const long long want_warps = (long long)sm_count * 8;
-  if (p.N / 32 >= want_warps) return launch_one<32, STEP>(p, sm_count, stream);
-  if (p.N / 16 >= want_warps) return launch_one<16, STEP>(p, sm_count, stream);
-  if (p.N / 8 >= want_warps) return launch_one<8, STEP>(p, sm_count, stream);
-  return launch_one<4, STEP>(p, sm_count, stream);
+  if (p.N / 32 >= want_warps) return launch_group_kernel<32, STEP>(p, sm_count, stream);
+  if (p.N / 16 >= want_warps) return launch_group_kernel<16, STEP>(p, sm_count, stream);
+  if (p.N / 8 >= want_warps) return launch_group_kernel<8, STEP>(p, sm_count, stream);
+  return launch_group_kernel<4, STEP>(p, sm_count, stream);
+}
+
+const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
+  int choice = g_kernel_choice;
+  if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 1;
+  if (choice == 2) return "merlin::env_kernel_warp<true>";
+  if (choice == 3)
+    return n_envs >= sm_count * 64 ? "merlin::env_kernel_tile<32,true>"
+                                   : (n_envs >= sm_count * 32 ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>");
+  const long long want_warps = (long long)sm_count * 8;
+  if (n_envs / 32 >= want_warps) return "merlin::env_kernel<32,true>";
+  if (n_envs / 16 >= want_warps) return "merlin::env_kernel<16,true>";
+  if (n_envs / 8 >= want_warps) return "merlin::env_kernel<8,true>";
+  return "merlin::env_kernel<4,true>";
 }
 
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream) {

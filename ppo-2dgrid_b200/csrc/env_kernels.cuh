@@ -8,16 +8,11 @@
 
 namespace merlin {
 
-#ifndef MERLIN_THREADS
-#define MERLIN_THREADS 256
+constexpr int kThreads = 256;                 // 8 warps per CTA
+// automatic kernel choice for RGB observations (1 group / 2 warp / 3 tile), from the B200 sweep in profiles/
+#ifndef MERLIN_AUTO_RGB_CHOICE
+#define MERLIN_AUTO_RGB_CHOICE(N, SMS) ((N) <= 8192 ? 2 : 3)
 #endif
-#ifndef MERLIN_MIN_BLOCKS
-#define MERLIN_MIN_BLOCKS 1
-#endif
-#ifndef MERLIN_LUT_SMEM
-#define MERLIN_LUT_SMEM 0
-#endif
-constexpr int kThreads = MERLIN_THREADS;      // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
 constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576
 constexpr int kKindStride = 52;               // 49 tile kinds per env, padded: odd word stride -> conflict-free lanes
@@ -26,8 +21,7 @@ constexpr int kChunksPerLane = (kChunks + 31) / 32;     // 19
 __host__ __device__ constexpr int warp_smem_bytes(int G) {
   return (G * kKindStride + G * kSymBytes + 15) & ~15;
 }
-constexpr int kLutBytes = MERLIN_LUT_SMEM ? kChunksPerLane * 32 * 4 : 0;   // blit map shared by all warps
-__host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + kLutBytes + kWarps * warp_smem_bytes(G); }
+__host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + kWarps * warp_smem_bytes(G); }
 
 struct EnvParams {
   // geometry / behaviour
@@ -42,6 +36,8 @@ struct EnvParams {
   const uint8_t* pool_cells;   // [L][cell_stride]
   const uint32_t* pool_agent;  // [L] x | y<<8 | dir<<16
   const uint8_t* atlas;        // [128][192]
+  const uint32_t* blit_lut;    // [kChunksPerLane][32] chunk -> (cell0, off0, cell1, off1), see chunk_lut()
+  uint32_t tile_present[4];    // bit t set: atlas slot t can appear in a frame of this handle's layout pool
   unsigned long long* bad_actions;
   // caller-owned I/O
   const int64_t* actions;
@@ -56,6 +52,9 @@ struct EnvParams {
   uint8_t* out_stuck;
 };
 
+// kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile
+void set_kernel_choice(int choice);
+const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,

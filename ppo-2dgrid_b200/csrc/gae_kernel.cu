@@ -29,22 +29,45 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
   float gae = 0.f;
   // gamma * next_val for t = T-1: python double product, rounded to f32 when it meets the f32 mask
   float gnext = (float)(gamma * (double)last_val[n]);
-  size_t k = (size_t)(T - 1) * N + n;
-#pragma unroll 4
-  for (int t = T - 1; t >= 0; --t, k -= N) {
+  // The recurrence is serial in t but its loads are not: fetch kChunk time steps (3 x kChunk independent, coalesced
+  // loads in flight per thread) before running the kChunk dependent updates, so a short rollout (a few thousand envs,
+  // one warp per SM) is bound by the arithmetic chain rather than by kChunk-times-fewer memory round trips.
+  constexpr int kChunk = 8;
+  int t = T - 1;
+  for (; t >= kChunk - 1; t -= kChunk) {
+    float r[kChunk], v[kChunk], d[kChunk];
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      const size_t k = (size_t)(t - j) * N + n;
+      r[j] = __ldcs(rew + k); v[j] = __ldcs(val + k); d[j] = __ldcs(done + k);
+    }
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      const size_t k = (size_t)(t - j) * N + n;
+      const float mask = __fsub_rn(1.0f, d[j]);
+      const float delta = __fsub_rn(__fadd_rn(r[j], __fmul_rn(gnext, mask)), v[j]);
+      gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, mask), gae));
+      __stcs(adv + k, gae);
+      __stcs(ret + k, __fadd_rn(v[j], gae));
+      gnext = __fmul_rn(g32, v[j]);  // gamma * values[t] is the next_val term of step t-1
+    }
+  }
+  for (; t >= 0; --t) {
+    const size_t k = (size_t)t * N + n;
     const float r = rew[k], v = val[k], d = done[k];
     const float mask = __fsub_rn(1.0f, d);
     const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gnext, mask)), v);
     gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl32, mask), gae));
     adv[k] = gae;
     ret[k] = __fadd_rn(v, gae);
-    gnext = __fmul_rn(g32, v);  // gamma * values[t] is next_val term of step t-1
+    gnext = __fmul_rn(g32, v);
   }
 }
 
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream) {
-  const int threads = 128;
+  // small rollouts: 32-thread blocks spread the envs over more SMs (4096 envs -> 128 blocks instead of 32)
+  const int threads = N >= 128 * 148 * 4 ? 128 : 32;
   const int blocks = (N + threads - 1) / threads;
   gae_kernel<<<blocks, threads, 0, stream>>>(rew, val, done, last_val, adv, ret, T, N, gamma, (float)gamma,
                                              (float)(gamma * lam));

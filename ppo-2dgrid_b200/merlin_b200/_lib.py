@@ -18,7 +18,8 @@ F_AUTO_RESET, F_RESET_SAME, F_SEVEN_ACTIONS, F_STUCK_PENALTY, F_EXPLORE_BONUS = 
 EXPORTS = (
     "merlin_env_default_config", "merlin_env_create", "merlin_env_destroy", "merlin_env_upload_layouts",
     "merlin_env_set_tile_atlas", "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step",
-    "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count", "merlin_gae",
+    "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
+    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_gae",
     "merlin_pack_cell", "merlin_last_error", "merlin_version",
 )
 
@@ -62,6 +63,10 @@ def load():
     lib.merlin_env_bad_actions.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.merlin_env_launch_count.argtypes = [vp]
     lib.merlin_env_launch_count.restype = i64
+    lib.merlin_set_kernel_choice.argtypes = [C.c_int]
+    lib.merlin_set_kernel_choice.restype = C.c_int
+    lib.merlin_env_step_kernel.argtypes = [vp, C.c_int]
+    lib.merlin_env_step_kernel.restype = C.c_char_p
     lib.merlin_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp]
     lib.merlin_pack_cell.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.merlin_pack_cell.restype = C.c_uint8
@@ -72,7 +77,14 @@ def load():
                  "merlin_env_read_state", "merlin_env_bad_actions", "merlin_gae"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
+    if os.environ.get("MERLIN_KERNEL_CHOICE"):
+        check(lib.merlin_set_kernel_choice(int(os.environ["MERLIN_KERNEL_CHOICE"])))
     return lib
+
+
+def set_kernel_choice(choice):
+    """0 = automatic, 1 = group kernel, 2 = warp-per-env kernel, 3 = CTA-tile kernel (process-wide; identical results)."""
+    check(load().merlin_set_kernel_choice(int(choice)))
 
 
 def check(rc):

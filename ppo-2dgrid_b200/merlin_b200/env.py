@@ -21,6 +21,21 @@ OBS_SHAPE = (VIEW * TILE, VIEW * TILE, 3)
 SYM_SHAPE = (VIEW, VIEW, 3)
 
 
+class StepBuffers:
+    """Caller-owned per-step outputs of `BatchedMerlinEnv.step` (all `[N]`, on the env's device)."""
+
+    def __init__(self, num_envs, device):
+        N, dev = num_envs, device
+        self.reward = torch.empty(N, dtype=torch.float32, device=dev)
+        self.terminated = torch.empty(N, dtype=torch.bool, device=dev)
+        self.truncated = torch.empty(N, dtype=torch.bool, device=dev)
+        self.episode_return = torch.empty(N, dtype=torch.float32, device=dev)
+        self.episode_length = torch.empty(N, dtype=torch.int32, device=dev)
+        self.stuck = torch.empty(N, dtype=torch.bool, device=dev)
+        self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
+                                       self.stuck.data_ptr())
+
+
 class BatchedMerlinEnv:
     def __init__(self, num_envs, cells=None, agent=None, *, enc=None, width=None, height=None, max_steps=None,
                  device="cuda", n_actions=3, auto_reset=True, reset_mode="next", stuck_penalty=False,
@@ -86,6 +101,12 @@ class BatchedMerlinEnv:
         self.stuck = torch.empty(N, dtype=torch.bool, device=dev)
         self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
                                        self.stuck.data_ptr())
+        self.n_envs = self.num_envs
+
+    def make_step_buffers(self):
+        """A private set of per-step outputs (reward, flags, episode stats) for `step(..., out=...)`: lets a caller keep
+        several steps in flight (e.g. copy step i's results to the host while step i+1 runs)."""
+        return StepBuffers(self.num_envs, self.device)
 
     # ---- pool ------------------------------------------------------------------------------------
     def upload_layouts(self, cells, agent):
@@ -123,7 +144,7 @@ class BatchedMerlinEnv:
                                               sym.data_ptr() if sym is not None else None, self._stream()))
         return obs, sym
 
-    def step(self, actions, out_obs=None, out_symbolic=None):
+    def step(self, actions, out_obs=None, out_symbolic=None, out=None):
         """actions: int64 CUDA tensor [N] (numpy/int lists are copied over).  Returns the gymnasium 5-tuple
         (obs u8[N,56,56,3], reward f32[N], terminated bool[N], truncated bool[N], info) with device tensors that
         are REUSED by the next call unless `out_obs` / `out_symbolic` point into caller storage (e.g. a rollout slot)."""
@@ -135,13 +156,14 @@ class BatchedMerlinEnv:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
         obs = out_obs if out_obs is not None else self.obs
         sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
+        b = out if out is not None else self
         _lib.check(self._lib.merlin_env_step(
             self._h, actions.data_ptr(), obs.data_ptr() if obs is not None else None,
-            sym.data_ptr() if sym is not None else None, self.reward.data_ptr(), self.terminated.data_ptr(),
-            self.truncated.data_ptr(), C.byref(self._extras), self._stream()))
-        info = {"episode_return": self.episode_return, "episode_length": self.episode_length, "stuck": self.stuck,
+            sym.data_ptr() if sym is not None else None, b.reward.data_ptr(), b.terminated.data_ptr(),
+            b.truncated.data_ptr(), C.byref(b._extras), self._stream()))
+        info = {"episode_return": b.episode_return, "episode_length": b.episode_length, "stuck": b.stuck,
                 "obs_symbolic": sym}
-        return obs, self.reward, self.terminated, self.truncated, info
+        return obs, b.reward, b.terminated, b.truncated, info
 
     # ---- state views (synchronous host copies; debugging / tests / gym adapter) ------------------
     def state_numpy(self):
@@ -172,6 +194,10 @@ class BatchedMerlinEnv:
         n = C.c_uint64()
         _lib.check(self._lib.merlin_env_bad_actions(self._h, C.byref(n)))
         return n.value
+
+    def step_kernel(self):
+        """Name of the CUDA kernel `step` launches for this batch size / observation mode."""
+        return self._lib.merlin_env_step_kernel(self._h, 1 if self.want_rgb else 0).decode()
 
     def launch_count(self):
         return int(self._lib.merlin_env_launch_count(self._h))

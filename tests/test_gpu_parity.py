@@ -16,6 +16,15 @@ from oracle import fast
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 2, 3], ids=["group_kernel", "warp_kernel", "tile_kernel"])
+def kernel_choice(request):
+    """Every parity test runs against all three step kernels (warp owns a group / warp per env / CTA tile)."""
+    from merlin_b200 import set_kernel_choice
+    set_kernel_choice(request.param)
+    yield request.param
+    set_kernel_choice(0)
+
+
 def _mods():
     from merlin_b200 import BatchedMerlinEnv, codes, gae, layouts, tiles
     return BatchedMerlinEnv, codes, gae, layouts, tiles

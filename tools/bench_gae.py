@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     import torch
-    from merlin_b200 import gae
+    from merlin_b200 import _lib, gae
 
     dev = torch.device("cuda", 0)
     try:
@@ -37,17 +37,29 @@ def main():
         val = torch.randn(T, N, device=dev)
         done = (torch.rand(T, N, device=dev) < 0.01).float()
         last = torch.randn(N, device=dev)
+        adv, ret = gae(rew, val, done, last)
+        lib = _lib.load()
+        stream = torch.cuda.current_stream().cuda_stream
+
+        def call():  # the C-ABI entry point on preallocated outputs (the Python wrapper adds ~30 us of host time)
+            _lib.check(lib.merlin_gae(rew.data_ptr(), val.data_ptr(), done.data_ptr(), last.data_ptr(), adv.data_ptr(),
+                                      ret.data_ptr(), T, N, 0.99, 0.95, stream))
         for _ in range(3):
-            gae(rew, val, done, last)
+            call()
         torch.cuda.synchronize()
         reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        big = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if T * N * 20 < (200 << 20) else None
+        times = []
         for _ in range(reps):
-            gae(rew, val, done, last)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps  # includes the two output allocations of the host wrapper
+            if big is not None:
+                big.zero_()  # flush L2 for the sizes that would otherwise be served from it
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sorted(times)[reps // 2]
         nbytes = 20 * T * N + 4 * N
         rows.append({"T": T, "N": N, "ms": ms, "algorithmic_mb": nbytes / 1e6, "achieved_gbs": nbytes / ms / 1e6,
                      "frac_of_hbm_peak": nbytes / ms / 1e6 / peak})
