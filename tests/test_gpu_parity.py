@@ -80,9 +80,9 @@ def _compare_batched(N, enc, agent, steps, n_actions=3, seed=0, check_every=1, *
     return env, ref, n_done
 
 
-@pytest.mark.parametrize("N", [1, 37, 4096, 10000, 20000, 40000])
+@pytest.mark.parametrize("N", [1, 31, 33, 37, 4096, 6000, 10000, 20000, 40000])
 def test_random_rollout_all_group_sizes(N):
-    """Covers every kernel instantiation (G = 4, 8, 16, 32), ragged tails and many auto-resets."""
+    """Covers every kernel instantiation (groups of 4/8/16/32, tiles of 8/16/32), ragged tails and many auto-resets."""
     _, codes, _, layouts, _ = _mods()
     L = 257
     cells, agent = layouts.generate("mediumhard", 16, range(5000, 5000 + L))
@@ -99,6 +99,35 @@ def test_random_rollout_other_difficulties_and_sizes(diff, size):
     cells, agent = layouts.generate(diff, size, range(100))
     enc = codes.unpack_to_encoding(cells, size, size)
     _compare_batched(512, enc, agent, 50, max_steps=17, seed=size)
+
+
+def _rect_layouts(rng, L, W, H, wall_p=0.15):
+    """Random W x H rooms (W != H allowed): border walls, random interior walls, one goal when there is room."""
+    enc = np.zeros((L, W, H, 3), np.uint8)
+    enc[..., 0] = 1
+    enc[:, 0, :, :] = enc[:, -1, :, :] = enc[:, :, 0, :] = enc[:, :, -1, :] = (2, 5, 0)
+    agent = np.zeros((L, 3), np.int32)
+    for l in range(L):
+        inner = rng.random((W - 2, H - 2)) < wall_p
+        enc[l, 1:-1, 1:-1][inner] = (2, 5, 0)
+        free = np.argwhere(enc[l, :, :, 0] == 1)
+        if len(free) == 0:
+            enc[l, 1, 1] = (1, 0, 0)
+            free = np.array([[1, 1]])
+        k = rng.permutation(len(free))
+        agent[l] = (free[k[0]][0], free[k[0]][1], rng.integers(0, 4))
+        if len(free) > 1:
+            enc[l, free[k[1]][0], free[k[1]][1]] = (8, 1, 0)
+    return enc, agent
+
+
+@pytest.mark.parametrize("W,H,N", [(3, 3, 40), (5, 12, 97), (19, 7, 97), (64, 64, 333), (255, 255, 65), (255, 4, 65)])
+def test_non_square_minimum_and_maximum_grid_sizes(W, H, N):
+    """Grid extents from the 3x3 minimum to the 255x255 maximum of the packed pose, W != H included."""
+    rng = np.random.default_rng(W * 1000 + H)
+    enc, agent = _rect_layouts(rng, 24 if W * H < 10000 else 6, W, H)
+    _compare_batched(N, enc, agent, 40, max_steps=13, seed=W + H)
+    _compare_batched(N, enc, agent, 12, n_actions=7, max_steps=9, seed=W)
 
 
 def _object_layouts(rng, L, size):
