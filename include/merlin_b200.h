@@ -15,6 +15,8 @@
  *   merlin_env_step               env.step(a)   src/ppo.py:76 ; src/fomaml.py:71 -- through
  *                                 ThreeActionWrapper (src/wrappers/three_action_wrapper.py:10-17),
  *                                 optionally StuckPenaltyWrapper (src/wrappers/stuck_penalty_wrapper.py:29-58)
+ *   merlin_env_render             RGBImgPartialObsWrapper.observation on stored symbolic observations (batched,
+ *                                 gathered) -- the read side of a compact RolloutBuffer (src/rollout_buffer.py:3-32)
  *   merlin_gae                    PPO.compute_gae src/ppo.py:107-120 ; FOMAML src/fomaml.py:116-123
  *
  * Conventions
@@ -98,6 +100,16 @@ int merlin_env_reset(merlin_env_t* h, const uint8_t* mask, uint8_t* obs_rgb, uin
  * Out-of-range actions are executed as `done` (no-op) and counted (merlin_env_bad_actions). */
 int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
                     uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream);
+
+/* Frames from STORED symbolic observations -- RGBImgPartialObsWrapper.observation (get_frame(tile_size=8,
+ * agent_pov=True), src/scenario_creator/scenario_creator.py:48) as a batch op with an optional row gather, so a
+ * rollout can keep the 147-byte symbolic image per step and expand minibatches on read (the reference's RolloutBuffer
+ * keeps 37 632 B of float32 per step, src/rollout_buffer.py:5).  obs_sym: DEVICE u8[n_rows][7][7][3] as step()/reset()
+ * write them; index: DEVICE i64[m] row numbers or NULL (= rows 0..m-1); out: DEVICE u8[m][9408].
+ * blocked = 0: u8[m][56][56][3], identical to the obs_rgb of step();  blocked = 1: u8[m][14][14][48], every 4x4 pixel
+ * block contiguous with channel index c*16 + dy*4 + dx (space-to-depth; what the actor-critic's first layer reads). */
+int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
+                      uint8_t* out, int32_t blocked, void* stream);
 
 /* State views: DEVICE pointers owned by the handle (valid until destroy). */
 int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state_xyds /* int4[N]: pose,step_count,cursor,stuck */,

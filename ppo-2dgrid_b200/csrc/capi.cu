@@ -60,6 +60,8 @@ struct merlin_env {
   uint32_t* pool_agent = nullptr;
   uint8_t* atlas = nullptr;
   uint32_t* blit_lut = nullptr;
+  uint8_t* atlas_blocked = nullptr;      // the atlas with every tile re-laid as four 4x4-pixel, channel-major blocks
+  uint32_t* blit_lut_blocked = nullptr;
   uint32_t tile_present[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
   unsigned long long* bad_actions = nullptr;
 };
@@ -123,6 +125,8 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
   ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->atlas_blocked, kAtlasBytes) == cudaSuccess;
   if (ok && h->mutable_grid) ok = cudaMalloc(&h->cells, N * h->cell_stride) == cudaSuccess;
   if (ok && (cfg->flags & MERLIN_F_EXPLORE_BONUS)) ok = cudaMalloc(&h->visited, N * h->vis_words * sizeof(uint32_t)) == cudaSuccess;
   if (!ok) {
@@ -138,6 +142,9 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
     uint32_t lut[kChunksPerLane * 32];
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
     cudaMemcpy(h->blit_lut, lut, sizeof lut, cudaMemcpyHostToDevice);
+    for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut_blocked(c) : 0u;
+    cudaMemcpy(h->blit_lut_blocked, lut, sizeof lut, cudaMemcpyHostToDevice);
+    cudaMemset(h->atlas_blocked, 0, kAtlasBytes);
   }
   if (h->cells) cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride);
   if (h->visited) cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t));
@@ -151,7 +158,7 @@ int merlin_env_destroy(merlin_env_t* h) {
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
   cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
-  cudaFree(h->blit_lut);
+  cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked);
   delete h;
   return MERLIN_OK;
 }
@@ -206,6 +213,16 @@ int merlin_env_set_tile_atlas(merlin_env_t* h, const uint8_t* tiles, int32_t n_t
   DeviceGuard guard(h->cfg.device);
   cudaError_t err = cudaMemcpy(h->atlas, tiles, kAtlasBytes, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) return cuda_fail(err, "atlas upload");
+  // blocked copy: tile[py][px][c] -> [sub = (py/4)*2 + px/4][c*16 + (py%4)*4 + px%4]
+  std::vector<uint8_t> blocked(kAtlasBytes);
+  for (int t = 0; t < kAtlasTiles; ++t)
+    for (int py = 0; py < kTile; ++py)
+      for (int px = 0; px < kTile; ++px)
+        for (int c = 0; c < 3; ++c)
+          blocked[(size_t)t * kTileBytes + ((py >> 2) * 2 + (px >> 2)) * 48 + c * 16 + (py & 3) * 4 + (px & 3)] =
+              tiles[(size_t)t * kTileBytes + (py * kTile + px) * 3 + c];
+  err = cudaMemcpy(h->atlas_blocked, blocked.data(), kAtlasBytes, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cuda_fail(err, "blocked atlas upload");
   h->has_atlas = true;
   return MERLIN_OK;
 }
@@ -257,6 +274,25 @@ int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, u
   if (extras) { p.out_ep_return = extras->episode_return; p.out_ep_length = extras->episode_length; p.out_stuck = extras->stuck; }
   cudaError_t err = launch_env_step(p, h->sm_count, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "env step launch");
+  h->launches += 1;
+  return MERLIN_OK;
+}
+
+int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
+                      uint8_t* out, int32_t blocked, void* stream) {
+  if (!h || !obs_sym || !out) return fail(MERLIN_EINVAL, "merlin_env_render: null argument");
+  if (m < 0 || n_rows < 0) return fail(MERLIN_EINVAL, "merlin_env_render: negative size");
+  if (!h->has_atlas) return fail(MERLIN_ESTATE, "frames requested before the tile atlas was set");
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(MERLIN_EINVAL, "out must be 16-byte aligned");
+  if (!index && n_rows && m > n_rows) return fail(MERLIN_EINVAL, "merlin_env_render: more frames than observation rows");
+  DeviceGuard guard(h->cfg.device);
+  RenderParams p{};
+  p.sym = obs_sym; p.index = index; p.out = out; p.M = m; p.n_rows = n_rows;
+  p.atlas = blocked ? h->atlas_blocked : h->atlas;
+  p.lut = blocked ? h->blit_lut_blocked : h->blit_lut;
+  for (int i = 0; i < 4; ++i) p.tile_present[i] = h->tile_present[i];
+  cudaError_t err = launch_render(p, blocked != 0, h->sm_count, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "render launch");
   h->launches += 1;
   return MERLIN_OK;
 }

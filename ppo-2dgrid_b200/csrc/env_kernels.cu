@@ -34,6 +34,15 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+constexpr int kWarpKindStride = 64;   // per-warp slot for the 49 tile kinds of one env
+
+// bit `tile` of a 128-bit mask held in four kernel-parameter words (no dynamic indexing: stays in constant memory)
+__device__ __forceinline__ bool tile_bit(const uint32_t (&m)[4], int tile) {
+  const int w = tile >> 5;
+  const uint32_t word = w == 0 ? m[0] : (w == 1 ? m[1] : (w == 2 ? m[2] : m[3]));
+  return (word >> (tile & 31)) & 1u;
+}
+
 struct Flags {
   int n_actions;
   bool mutable_grid, stuck_on, explore_on, auto_reset, advance, want_rgb, want_sym;
@@ -51,7 +60,7 @@ __device__ __forceinline__ void stage_atlas(const EnvParams& p, uint8_t* atlas_s
   int4* dst = reinterpret_cast<int4*>(atlas_s);
   for (int i = threadIdx.x; i < kAtlasBytes / 16; i += blockDim.x) {
     const int tile = i / (kTileBytes / 16);
-    if ((p.tile_present[tile >> 5] >> (tile & 31)) & 1u) dst[i] = __ldg(src + i);
+    if (tile_bit(p.tile_present, tile)) dst[i] = __ldg(src + i);
   }
 }
 
@@ -313,7 +322,6 @@ __global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvPara
 //   * the 49-cell window is gathered two cells per lane; transparency goes through two warp ballots into the same
 //     49-bit mask the visibility routine consumes; every lane then knows the visibility of its own cells.
 constexpr int kWarpKernelThreads = 256;
-constexpr int kWarpKindStride = 64;
 
 template <bool STEP>
 __global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const EnvParams p) {
@@ -452,6 +460,72 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const E
     if (f.want_rgb) blit_frame(atlas_s, kp, lut, p.obs_rgb + (size_t)e * kImgBytes, lane);
     __syncwarp();  // kp is reused by this warp's next env
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// render_kernel<BLOCKED>: frames from stored symbolic observations, one warp per frame, optional row gather.
+// Rollouts can then keep 147 B per step instead of 9408 B and expand minibatches on read.
+template <bool BLOCKED>
+__global__ void __launch_bounds__(256, 2) render_kernel(const RenderParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  uint8_t* atlas_s = smem;
+  uint8_t* kp = smem + kAtlasBytes + warp * kWarpKindStride;
+  {
+    const int4* src = reinterpret_cast<const int4*>(p.atlas);
+    int4* dst = reinterpret_cast<int4*>(atlas_s);
+    for (int i = threadIdx.x; i < kAtlasBytes / 16; i += blockDim.x) {
+      const int tile = i / (kTileBytes / 16);
+      if (tile_bit(p.tile_present, tile)) dst[i] = __ldg(src + i);
+    }
+  }
+  uint32_t lut[kChunksPerLane];
+#pragma unroll
+  for (int k = 0; k < kChunksPerLane; ++k) lut[k] = __ldg(p.lut + k * 32 + lane);
+  __syncthreads();
+
+  for (int m = blockIdx.x * warps_per_cta + warp; m < p.M; m += gridDim.x * warps_per_cta) {
+    long long row = p.index ? p.index[m] : m;
+    if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;  // never read outside the buffer; callers validate indices
+    const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = lane + 32 * h;  // cell index vi*7 + vj, the order Grid.encode stores them
+      if (k < kCells) {
+        const uint32_t t = sym[3 * k], c = sym[3 * k + 1], st = sym[3 * k + 2];
+        kp[k] = (uint8_t)kind_of_sym(t, c, st, k == (kView / 2) * kView + (kView - 1));
+      }
+    }
+    __syncwarp();
+    uint8_t* frame = p.out + (size_t)m * kImgBytes;
+    if (BLOCKED) {
+      const uint4* atlas128 = reinterpret_cast<const uint4*>(atlas_s);
+#pragma unroll
+      for (int k = 0; k < kChunksPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < kChunks) {
+          const uint32_t q = lut[k];
+          const uint4 v = atlas128[kp[q & 0xff] * (kTileBytes / 16) + (q >> 8)];
+          st_stream_v4(frame + c * 16, v.x, v.y, v.z, v.w);
+        }
+      }
+    } else {
+      blit_frame(atlas_s, kp, lut, frame, lane);
+    }
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream) {
+  if (p.M <= 0) return cudaSuccess;
+  constexpr int threads = 256, warps = threads / 32;
+  const size_t smem = kAtlasBytes + warps * kWarpKindStride;
+  const int grid = min(sm_count * 2, (p.M + warps - 1) / warps);
+  if (blocked) render_kernel<true><<<grid, threads, smem, stream>>>(p);
+  else render_kernel<false><<<grid, threads, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -57,6 +57,21 @@ void set_kernel_choice(int choice);
 const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream);
+// Frames from stored symbolic observations (RGBImgPartialObsWrapper.observation as a batch op, with an optional
+// row gather): out[m] = frame(sym[index ? index[m] : m]).  blocked = false: u8[M][56][56][3] as the env kernel writes
+// them; blocked = true: u8[M][14][14][48], every 4x4 pixel block contiguous with channel index c*16 + dy*4 + dx (the
+// layout the actor-critic's first layer consumes).  `atlas` / `lut` must be the pair matching `blocked`.
+struct RenderParams {
+  const uint8_t* sym;        // [*][147]
+  const int64_t* index;      // [M] or nullptr
+  uint8_t* out;              // [M][9408]
+  const uint8_t* atlas;      // [128][192]
+  const uint32_t* lut;       // [kChunksPerLane][32]
+  uint32_t tile_present[4];
+  int M;
+  long long n_rows;          // rows of `sym` (index bound), 0 = unchecked
+};
+cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream);
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream);
 

@@ -221,4 +221,27 @@ MERLIN_HD uint32_t chunk_lut(int c) {
   return packed;
 }
 
+// Chunk lookup for the BLOCKED frame layout u8[14][14][48] (4x4 pixel blocks, channel-major inside a block): 16-byte
+// chunk c = part (c % 3) of block b = c / 3 at (by, bx) = (b / 14, b % 14); the block lies inside cell
+// (vi, vj) = (bx / 2, by / 2) as its sub-block (by % 2, bx % 2).  Returns cell | unit16 << 8 with unit16 the 16-byte
+// unit inside the blocked 192-byte tile (sub * 3 + part).
+MERLIN_HD uint32_t chunk_lut_blocked(int c) {
+  const int b = c / 3, part = c - b * 3;
+  const int by = b / (kView * 2), bx = b - by * (kView * 2);
+  const int vi = bx >> 1, vj = by >> 1, sub = ((by & 1) << 1) | (bx & 1);
+  return (uint32_t)(vi * kView + vj) | ((uint32_t)(sub * 3 + part) << 8);
+}
+
+// Tile kind shown for a cell of a stored symbolic observation (Grid.encode triple); `agent_cell` = view cell (3, 6).
+MERLIN_HD uint32_t kind_of_sym(uint32_t t, uint32_t c, uint32_t st, bool agent_cell) {
+  uint32_t code = 0;  // (0,0,0) = not visible
+  if (t != 0) {
+    uint32_t tt = t & 0xf;
+    if (tt == 4) tt = st == 1 ? T_DOOR_CLOSED : (st == 2 ? T_DOOR_LOCKED : T_DOOR_OPEN);
+    code = tt | ((c & 7) << 4);
+  }
+  if (agent_cell) return agent_kind((code & 0xf) == T_EMPTY ? 0u : code);  // the cell under the agent shows what it carries
+  return code;
+}
+
 }  // namespace merlin

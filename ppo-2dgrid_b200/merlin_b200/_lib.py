@@ -19,7 +19,7 @@ EXPORTS = (
     "merlin_env_default_config", "merlin_env_create", "merlin_env_destroy", "merlin_env_upload_layouts",
     "merlin_env_set_tile_atlas", "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step",
     "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
-    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_gae",
+    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_env_render", "merlin_gae",
     "merlin_pack_cell", "merlin_last_error", "merlin_version",
 )
 
@@ -65,6 +65,8 @@ def load():
     lib.merlin_env_launch_count.restype = i64
     lib.merlin_set_kernel_choice.argtypes = [C.c_int]
     lib.merlin_set_kernel_choice.restype = C.c_int
+    lib.merlin_env_render.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    lib.merlin_env_render.restype = C.c_int
     lib.merlin_env_step_kernel.argtypes = [vp, C.c_int]
     lib.merlin_env_step_kernel.restype = C.c_char_p
     lib.merlin_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp]

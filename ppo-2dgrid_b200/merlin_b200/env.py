@@ -165,6 +165,32 @@ class BatchedMerlinEnv:
                 "obs_symbolic": sym}
         return obs, b.reward, b.terminated, b.truncated, info
 
+    def render(self, obs_symbolic, index=None, out=None, blocked=False):
+        """Frames from stored symbolic observations: `obs_symbolic` u8[R, 7, 7, 3] (any leading shape, contiguous),
+        `index` optional int64[M] rows to render (a minibatch gather fused with the rendering).
+        Returns u8[M, 56, 56, 3] (bit-identical to what `step` wrote for those states) or, with `blocked=True`,
+        u8[M, 14, 14, 48] (4x4 pixel blocks, channel-major: the actor-critic's space-to-depth input)."""
+        sym = obs_symbolic
+        if sym.dtype != torch.uint8 or sym.device != self.device or not sym.is_contiguous():
+            raise ValueError("obs_symbolic must be a contiguous uint8 tensor on the env's device")
+        rows = sym.numel() // (VIEW * VIEW * 3)
+        if index is not None:
+            if index.dtype != torch.int64 or index.device != self.device or not index.is_contiguous():
+                index = index.to(device=self.device, dtype=torch.int64).contiguous()
+            m = index.numel()
+        else:
+            m = rows
+        shape = (m, 2 * VIEW, 2 * VIEW, 48) if blocked else (m,) + OBS_SHAPE
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        elif out.numel() != m * VIEW * TILE * VIEW * TILE * 3 or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous uint8 tensor of m * 9408 bytes")
+        if m == 0:
+            return out
+        _lib.check(self._lib.merlin_env_render(self._h, sym.data_ptr(), rows, index.data_ptr() if index is not None else None,
+                                               m, out.data_ptr(), 1 if blocked else 0, self._stream()))
+        return out
+
     # ---- state views (synchronous host copies; debugging / tests / gym adapter) ------------------
     def state_numpy(self):
         """Host copy of the packed per-env state: dict of x, y, dir, carry, step_count, layout, stay, episode_return."""

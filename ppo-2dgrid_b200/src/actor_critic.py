@@ -103,7 +103,11 @@ class CNNActorCritic(_ActorCriticBase):
         return x.float()
 
     def _logits_value(self, obs):
-        if self.blocked_first_layer and obs.ndim == 4 and obs.shape[-1] == 3:
+        if obs.ndim == 4 and obs.shape[-1] == 48:
+            # frames already in the blocked layout u8[N, H/4, W/4, 48] (BatchedMerlinEnv.render(..., blocked=True))
+            xb = obs.permute(0, 3, 1, 2).float()
+            fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
+        elif self.blocked_first_layer and obs.ndim == 4 and obs.shape[-1] == 3:
             xb = space_to_depth4(obs)  # shared by both trunks
             fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
         else:

@@ -27,7 +27,8 @@ from .rollout_buffer import RolloutBuffer
 
 class PPO:
     def __init__(self, env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
-                 minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False):
+                 minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False,
+                 obs_storage="rgb"):
         self.env = env
         self.batched = isinstance(env, BatchedMerlinEnv)
         self.device = env.device if self.batched else torch.device(device)
@@ -35,10 +36,15 @@ class PPO:
         self.update_epochs, self.batch_size, self.minibatch_size = update_epochs, batch_size, minibatch_size
         self.vf_coef, self.ent_coef = vf_coef, ent_coef
 
+        if obs_storage not in ("rgb", "symbolic"):
+            raise ValueError("obs_storage must be 'rgb' (56x56x3 frames in the rollout) or 'symbolic' (7x7x3, expanded on read)")
+        self.obs_storage = obs_storage if self.batched else "rgb"
         if self.batched:
             self.num_envs = env.num_envs
             act_dim = env.n_actions
             self.use_cnn, self.obs_shape = True, tuple(env.obs.shape[1:])
+            if self.obs_storage == "symbolic" and env.obs_symbolic is None:
+                raise ValueError("obs_storage='symbolic' needs an env created with want_symbolic=True")
         else:
             self.num_envs = 1
             sample_obs, _ = env.reset()
@@ -53,7 +59,10 @@ class PPO:
         self.optimizer = optim.Adam(self.ac.parameters(), lr=lr)
         self._grads = FlatOrNone(self.ac) if parallel.world_size() > 1 else None
 
-        self.buffer = RolloutBuffer(buffer_size=self.batch_size, obs_shape=self.obs_shape, device=self.device,
+        # 'symbolic': the rollout keeps the 147-byte Grid.encode image per step (64x smaller than the frame); minibatches
+        # are rendered on read by merlin_env_render, straight into the blocked layout the first conv layer consumes
+        stored_shape = (7, 7, 3) if self.obs_storage == "symbolic" else self.obs_shape
+        self.buffer = RolloutBuffer(buffer_size=self.batch_size, obs_shape=stored_shape, device=self.device,
                                     is_discrete=True, num_envs=self.num_envs,
                                     obs_dtype=torch.uint8 if self.batched else torch.float32)
         self.episode_returns = []
@@ -62,6 +71,10 @@ class PPO:
         if self.batched:
             T, N = self.buffer.horizon, self.num_envs
             self._last_obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=self.device)
+            if self.obs_storage == "symbolic":
+                self._last_sym = torch.zeros((N, 7, 7, 3), dtype=torch.uint8, device=self.device)
+                self._mb_frames = torch.zeros((min(self.minibatch_size, self.batch_size), 14, 14, 48), dtype=torch.uint8,
+                                              device=self.device)
             self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
             self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
             self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
@@ -84,11 +97,18 @@ class PPO:
 
     def _rollout_body(self):
         env, buf, T = self.env, self.buffer, self.buffer.horizon
-        env.reset(out_obs=buf.obs_slot(0))
+        sym = self.obs_storage == "symbolic"
+        if sym:  # frames live in one reusable buffer (the policy's input); the rollout receives the symbolic images
+            env.reset(out_obs=self._last_obs, out_symbolic=buf.obs_slot(0))
+        else:
+            env.reset(out_obs=buf.obs_slot(0))
         for t in range(T):
-            action, logp, value = self.ac.act(buf.obs_slot(t), deterministic=False)
-            nxt = buf.obs_slot(t + 1) if t + 1 < T else self._last_obs
-            _, rew, term, trunc, info = env.step(action, out_obs=nxt)
+            action, logp, value = self.ac.act(self._last_obs if sym else buf.obs_slot(t), deterministic=False)
+            nxt = buf.obs_slot(t + 1) if t + 1 < T else (self._last_sym if sym else self._last_obs)
+            if sym:
+                _, rew, term, trunc, info = env.step(action, out_obs=self._last_obs, out_symbolic=nxt)
+            else:
+                _, rew, term, trunc, info = env.step(action, out_obs=nxt)
             buf.actions[t].copy_(action)
             buf.logprobs[t].copy_(logp)
             buf.values[t].copy_(value)
@@ -108,7 +128,7 @@ class PPO:
                 side = torch.cuda.Stream(self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
-                    self.ac.act(self.buffer.obs_slot(0))
+                    self.ac.act(self._last_obs)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
@@ -159,7 +179,16 @@ class PPO:
         adv = (adv - mean) / (std + 1e-8)
 
         n = self.buffer.horizon * self.num_envs
-        states = states.reshape((n,) + self.obs_shape)
+        if self.obs_storage == "symbolic":
+            stored = states.reshape(n, 7, 7, 3)
+
+            def frames(mb):  # minibatch gather + rendering in one kernel
+                return self.env.render(stored, mb, out=self._mb_frames[: mb.numel()], blocked=True)
+        else:
+            stored = states.reshape((n,) + self.obs_shape)
+
+            def frames(mb):
+                return stored[mb]
         actions, logprobs_old = actions.reshape(n), logprobs_old.reshape(n)
         adv, returns = adv.reshape(n), returns.reshape(n)
 
@@ -169,7 +198,7 @@ class PPO:
             idxs = torch.randperm(n, device=self.device)
             for start in range(0, n, self.minibatch_size):
                 mb = idxs[start: start + self.minibatch_size]
-                logp_new, entropy, values = self.ac.evaluate(states[mb], actions[mb])
+                logp_new, entropy, values = self.ac.evaluate(frames(mb), actions[mb])
                 mb_adv, mb_old = adv[mb], logprobs_old[mb]
                 ratio = torch.exp(logp_new - mb_old)
                 surr = torch.min(ratio * mb_adv, torch.clamp(ratio, 1 - self.clip_eps, 1 + self.clip_eps) * mb_adv)

@@ -184,6 +184,35 @@ def test_batched_ppo_stored_logp_and_values_match_evaluate():
     agent.train(total_steps=2 * 32 * 4)  # reference PPO.train loop
 
 
+def test_ppo_symbolic_rollout_storage_equals_frame_storage():
+    """obs_storage='symbolic' keeps 147 B per step and renders minibatches on read: same rollout, same update."""
+    from src.actor_critic import space_to_depth4
+    from src.ppo import PPO
+    runs = {}
+    for mode in ("rgb", "symbolic"):
+        torch.manual_seed(9)
+        env = _sc().create_batched_env("hard", 48, device="cuda:0", seeds=range(96), max_steps=20, want_symbolic=True)
+        agent = PPO(env, batch_size=48 * 10, minibatch_size=96, update_epochs=2, ent_coef=0.05, obs_storage=mode)
+        lv = agent.collect_rollouts()
+        states, actions, logp, rewards, values, dones = agent.buffer.get()
+        frames = states if mode == "rgb" else env.render(states.reshape(-1, 7, 7, 3)).reshape(10, 48, 56, 56, 3)
+        if mode == "symbolic":
+            assert states.shape == (10, 48, 7, 7, 3)
+            blk = env.render(states.reshape(-1, 7, 7, 3), blocked=True)
+            ref_blk = space_to_depth4(frames.reshape(-1, 56, 56, 3)).permute(0, 2, 3, 1).to(torch.uint8)
+            assert torch.equal(blk, ref_blk)
+        metrics = agent.update(lv)
+        runs[mode] = (frames.clone(), actions.clone(), rewards.clone(), values.clone(), lv.clone(), metrics,
+                      [p.detach().clone() for p in agent.ac.parameters()])
+    a, b = runs["rgb"], runs["symbolic"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.allclose(a[3], b[3], atol=1e-6) and torch.allclose(a[4], b[4], atol=1e-6)
+    for k in a[5]:
+        assert abs(a[5][k] - b[5][k]) < 1e-4 * max(1.0, abs(a[5][k])), (k, a[5][k], b[5][k])
+    for pa, pb in zip(a[6], b[6]):
+        assert torch.allclose(pa, pb, atol=1e-5)
+
+
 def test_single_env_ppo_reference_loop_runs_on_the_cuda_env():
     from src.ppo import PPO
     torch.manual_seed(0)

@@ -337,3 +337,48 @@ def test_step_writes_into_rollout_slot_and_cuda_graph():
         graph.replay()
         robs, rr, *_ = ref2.step(_np(acts[t]))
         assert np.array_equal(_np(env2.obs), robs) and np.array_equal(_np(env2.reward), rr)
+
+
+# ---- frames from stored symbolic observations (merlin_env_render) -----------------------------------------
+def _blocked_of(rgb):
+    """Reference layout transform on the host: u8[M,56,56,3] -> u8[M,14,14,48], channel index c*16 + dy*4 + dx."""
+    m = rgb.shape[0]
+    return rgb.reshape(m, 14, 4, 14, 4, 3).transpose(0, 1, 3, 5, 2, 4).reshape(m, 14, 14, 48)
+
+
+@pytest.mark.parametrize("n_actions", [3, 7])
+def test_render_from_symbolic_is_bit_identical_to_step_frames(n_actions):
+    """RGBImgPartialObsWrapper.observation on STORED symbolic images == the frames step() wrote, with and without a
+    row gather, in the reference layout and in the blocked (space-to-depth) layout; objects / carrying included."""
+    _, codes, _, layouts, _ = _mods()
+    rng = np.random.default_rng(11)
+    N, T = 300, 24
+    if n_actions == 3:
+        cells, agent = layouts.generate("hardest", 16, range(64))
+        enc = codes.unpack_to_encoding(cells, 16, 16)
+    else:
+        enc, agent = _object_layouts(rng, 64, 11)
+    env = _make_gpu_env(N, enc, agent, n_actions=n_actions, max_steps=15)
+    sym_store = torch.zeros((T + 1, N, 7, 7, 3), dtype=torch.uint8, device="cuda:0")
+    rgb_store = torch.zeros((T + 1, N, 56, 56, 3), dtype=torch.uint8, device="cuda:0")
+    env.reset(out_obs=rgb_store[0], out_symbolic=sym_store[0])
+    for t in range(T):
+        a = rng.integers(0, n_actions, N)
+        if n_actions == 7:
+            a = np.where(rng.random(N) < 0.3, 3, a)  # plenty of pickups so that carried objects show under the agent
+        env.step(torch.as_tensor(a, device="cuda:0"), out_obs=rgb_store[t + 1], out_symbolic=sym_store[t + 1])
+    if n_actions == 7:
+        assert int((env.state_numpy()["carry"] != 0).sum()) > 0
+    flat_rgb = rgb_store.reshape(-1, 56, 56, 3)
+    got = env.render(sym_store)  # all rows, reference layout
+    assert got.shape == flat_rgb.shape and torch.equal(got, flat_rgb)
+    idx = torch.as_tensor(rng.integers(0, flat_rgb.shape[0], 1000), device="cuda:0")  # gather with repeats
+    assert torch.equal(env.render(sym_store, idx), flat_rgb[idx])
+    blocked = env.render(sym_store, idx, blocked=True)
+    assert blocked.shape == (1000, 14, 14, 48)
+    assert np.array_equal(_np(blocked), _blocked_of(_np(flat_rgb[idx])))
+    out = torch.zeros((7, 56, 56, 3), dtype=torch.uint8, device="cuda:0")
+    assert env.render(sym_store, idx[:7], out=out).data_ptr() == out.data_ptr() and torch.equal(out, flat_rgb[idx[:7]])
+    with pytest.raises(ValueError):
+        env.render(sym_store.float())
+    assert env.render(sym_store[:0]).shape == (0, 56, 56, 3)

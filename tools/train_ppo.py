@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--layouts", type=int, default=65536)
     ap.add_argument("--eval-tasks", type=int, default=100)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="rgb",
+                    help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
     ap.add_argument("--cpu-baseline", action="store_true",
                     help="also time one reference-style PPO iteration (N=1, 2048 steps) on the host cores (oracle port)")
     ap.add_argument("--out", default=None)
@@ -75,10 +77,11 @@ def main():
     cells = np.concatenate([p[0] for p in parts])
     agent_xyd = np.concatenate([p[1] for p in parts])
     t_lay = time.perf_counter() - t_lay
-    env = sc.create_batched_env(a.difficulty, a.envs, device=dev, layouts=(cells, agent_xyd))
+    env = sc.create_batched_env(a.difficulty, a.envs, device=dev, layouts=(cells, agent_xyd),
+                                want_symbolic=a.obs_storage == "symbolic")
     agent = PPO(env, lr=a.lr, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=a.update_epochs,
                 batch_size=a.envs * a.horizon, minibatch_size=a.minibatch, vf_coef=0.5, ent_coef=a.ent_coef,
-                use_cuda_graph=not a.no_graph)
+                use_cuda_graph=not a.no_graph, obs_storage=a.obs_storage)
 
     def sync():
         if world > 1:
@@ -122,7 +125,9 @@ def main():
                "iterations": iters, "rollout_s": t_roll, "update_s": t_upd,
                "config": {"workload": f"configs[2]: PPO {a.difficulty} 16x16, {a.envs} envs/GPU x horizon {a.horizon}",
                           "minibatch": a.minibatch, "update_epochs": a.update_epochs, "lr": a.lr, "ent_coef": a.ent_coef,
-                          "cuda_graph_rollout": not a.no_graph, "layout_pool_per_gpu": per_rank,
+                          "cuda_graph_rollout": not a.no_graph, "obs_storage": a.obs_storage,
+                          "rollout_obs_bytes": int(agent.buffer.states.numel() * agent.buffer.states.element_size()),
+                          "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "layout_pool_per_gpu": per_rank,
                           "layout_gen_host_s": t_lay, "dtype": "fp32 policy (PyTorch), u8 frames", "seed": a.seed},
                "eval": {"tasks": a.eval_tasks, "seeds": "200000..", "mean_return": float(np.mean(r)),
                         "mean_steps": float(np.mean(n)), "success_rate": float(np.mean(g)), "eval_s": te},
