@@ -416,7 +416,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Keep fd 1 for the ONE JSON line: everything else that writes to stdout while the bench runs (NCCL's version
+    banner, library chatter of child processes) is sent to stderr; the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _claim_stdout()
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

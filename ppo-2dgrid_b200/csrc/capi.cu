@@ -62,7 +62,7 @@ struct merlin_env {
   uint32_t* blit_lut = nullptr;
   uint8_t* atlas_blocked = nullptr;      // the atlas with every tile re-laid as four 4x4-pixel, channel-major blocks
   uint32_t* blit_lut_blocked = nullptr;
-  uint32_t tile_present[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  uint32_t* tile_present = nullptr;      // [4] device words, rewritten by upload_layouts
   unsigned long long* bad_actions = nullptr;
 };
 
@@ -75,7 +75,7 @@ static EnvParams base_params(const merlin_env* h) {
   p.state = h->state; p.ep_return = h->ep_return; p.cells = h->cells; p.visited = h->visited;
   p.pool_cells = h->pool_cells; p.pool_agent = h->pool_agent; p.atlas = h->atlas; p.bad_actions = h->bad_actions;
   p.blit_lut = h->blit_lut;
-  for (int i = 0; i < 4; ++i) p.tile_present[i] = h->tile_present[i];
+  p.tile_present = h->tile_present;
   return p;
 }
 
@@ -127,6 +127,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas_blocked, kAtlasBytes) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->tile_present, 4 * sizeof(uint32_t)) == cudaSuccess;
   if (ok && h->mutable_grid) ok = cudaMalloc(&h->cells, N * h->cell_stride) == cudaSuccess;
   if (ok && (cfg->flags & MERLIN_F_EXPLORE_BONUS)) ok = cudaMalloc(&h->visited, N * h->vis_words * sizeof(uint32_t)) == cudaSuccess;
   if (!ok) {
@@ -145,6 +146,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut_blocked(c) : 0u;
     cudaMemcpy(h->blit_lut_blocked, lut, sizeof lut, cudaMemcpyHostToDevice);
     cudaMemset(h->atlas_blocked, 0, kAtlasBytes);
+    cudaMemset(h->tile_present, 0xff, 4 * sizeof(uint32_t));
   }
   if (h->cells) cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride);
   if (h->visited) cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t));
@@ -158,7 +160,7 @@ int merlin_env_destroy(merlin_env_t* h) {
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
   cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
-  cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked);
+  cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked); cudaFree(h->tile_present);
   delete h;
   return MERLIN_OK;
 }
@@ -190,20 +192,26 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
     agent[l] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)d << 16);
   }
   DeviceGuard guard(h->cfg.device);
-  uint8_t* d_cells = nullptr;
-  uint32_t* d_agent = nullptr;
-  if (cudaMalloc(&d_cells, packed.size()) != cudaSuccess || cudaMalloc(&d_agent, agent.size() * sizeof(uint32_t)) != cudaSuccess) {
-    cudaFree(d_cells);
-    return cuda_fail(cudaGetLastError(), "layout pool allocation");
-  }
-  cudaError_t err = cudaMemcpy(d_cells, packed.data(), packed.size(), cudaMemcpyHostToDevice);
-  if (err == cudaSuccess) err = cudaMemcpy(d_agent, agent.data(), agent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (err != cudaSuccess) { cudaFree(d_cells); cudaFree(d_agent); return cuda_fail(err, "layout upload"); }
-  cudaDeviceSynchronize();  // nothing may still be reading the old pool
-  cudaFree(h->pool_cells); cudaFree(h->pool_agent);
-  h->pool_cells = d_cells; h->pool_agent = d_agent; h->n_layouts = n_layouts;
   // pickup/drop/toggle create codes the pool does not hold (door states, carried objects): stage the whole atlas then
-  for (int i = 0; i < 4; ++i) h->tile_present[i] = h->mutable_grid ? 0xffffffffu : present[i];
+  if (h->mutable_grid) present[0] = present[1] = present[2] = present[3] = 0xffffffffu;
+  cudaError_t err = cudaDeviceSynchronize();  // nothing may still be reading the old pool
+  if (err != cudaSuccess) return cuda_fail(err, "layout upload (sync)");
+  if (n_layouts != h->n_layouts) {
+    // a pool of another size gets new storage; an equal-sized pool is overwritten in place, so device pointers (and
+    // CUDA graphs captured over them) stay valid across uploads
+    uint8_t* d_cells = nullptr;
+    uint32_t* d_agent = nullptr;
+    if (cudaMalloc(&d_cells, packed.size()) != cudaSuccess || cudaMalloc(&d_agent, agent.size() * sizeof(uint32_t)) != cudaSuccess) {
+      cudaFree(d_cells);
+      return cuda_fail(cudaGetLastError(), "layout pool allocation");
+    }
+    cudaFree(h->pool_cells); cudaFree(h->pool_agent);
+    h->pool_cells = d_cells; h->pool_agent = d_agent; h->n_layouts = n_layouts;
+  }
+  err = cudaMemcpy(h->pool_cells, packed.data(), packed.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(h->pool_agent, agent.data(), agent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(h->tile_present, present, sizeof present, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cuda_fail(err, "layout upload");
   h->was_reset = false;
   return merlin_env_set_cursors(h, nullptr);
 }
@@ -290,7 +298,7 @@ int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, c
   p.sym = obs_sym; p.index = index; p.out = out; p.M = m; p.n_rows = n_rows;
   p.atlas = blocked ? h->atlas_blocked : h->atlas;
   p.lut = blocked ? h->blit_lut_blocked : h->blit_lut;
-  for (int i = 0; i < 4; ++i) p.tile_present[i] = h->tile_present[i];
+  p.tile_present = h->tile_present;
   cudaError_t err = launch_render(p, blocked != 0, h->sm_count, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "render launch");
   h->launches += 1;

@@ -36,11 +36,10 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, ui
 
 constexpr int kWarpKindStride = 64;   // per-warp slot for the 49 tile kinds of one env
 
-// bit `tile` of a 128-bit mask held in four kernel-parameter words (no dynamic indexing: stays in constant memory)
-__device__ __forceinline__ bool tile_bit(const uint32_t (&m)[4], int tile) {
-  const int w = tile >> 5;
-  const uint32_t word = w == 0 ? m[0] : (w == 1 ? m[1] : (w == 2 ? m[2] : m[3]));
-  return (word >> (tile & 31)) & 1u;
+// bit `tile` of the 128-bit "present" mask (four device words, read through the read-only path; they live in device
+// memory rather than in the kernel parameters so that a captured CUDA graph sees a re-uploaded layout pool's mask)
+__device__ __forceinline__ bool tile_bit(const uint32_t* m, int tile) {
+  return (__ldg(m + (tile >> 5)) >> (tile & 31)) & 1u;
 }
 
 struct Flags {

@@ -37,7 +37,7 @@ struct EnvParams {
   const uint32_t* pool_agent;  // [L] x | y<<8 | dir<<16
   const uint8_t* atlas;        // [128][192]
   const uint32_t* blit_lut;    // [kChunksPerLane][32] chunk -> (cell0, off0, cell1, off1), see chunk_lut()
-  uint32_t tile_present[4];    // bit t set: atlas slot t can appear in a frame of this handle's layout pool
+  const uint32_t* tile_present;  // [4] device words; bit t set: atlas slot t can appear in a frame of this handle's pool
   unsigned long long* bad_actions;
   // caller-owned I/O
   const int64_t* actions;
@@ -67,7 +67,7 @@ struct RenderParams {
   uint8_t* out;              // [M][9408]
   const uint8_t* atlas;      // [128][192]
   const uint32_t* lut;       // [kChunksPerLane][32]
-  uint32_t tile_present[4];
+  const uint32_t* tile_present;  // [4] device words
   int M;
   long long n_rows;          // rows of `sym` (index bound), 0 = unchecked
 };

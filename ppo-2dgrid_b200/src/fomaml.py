@@ -55,6 +55,8 @@ class FOMAML:
         self.ent_coef = 0.05
         self.clip_eps = 0.2
         self._envs = {}  # task-batch size -> cached BatchedMerlinEnv
+        self._graphs = {}  # (env, steps, per-task weights?) -> captured rollout
+        self.use_cuda_graph = self.device.type == "cuda"
 
     # ---- helpers ------------------------------------------------------------------------------------------
     def _obs_to_tensor(self, state):
@@ -93,26 +95,67 @@ class FOMAML:
         Returns the reference's dict; batched tensors are time-major `[steps, B, ...]`."""
         if not isinstance(env, BatchedMerlinEnv):
             return self._collect_single(env, policy, steps, task_seed)
+        if self.use_cuda_graph and policy is self.meta_policy:
+            return self._collect_graphed(env, steps, params)
+        buf = self._rollout_buffers(env, steps)
+        self._rollout_body(env, policy, params, steps, buf)
+        return self._rollout_result(buf, steps)
+
+    def _rollout_buffers(self, env, steps):
         B, dev = env.num_envs, env.device
-        obs = torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev)
-        act = torch.empty((steps, B), dtype=torch.long, device=dev)
-        rew = torch.empty((steps, B), dtype=torch.float32, device=dev)
-        val = torch.empty_like(rew)
-        logp = torch.empty_like(rew)
-        done = torch.empty_like(rew)
-        ep_ret = torch.empty_like(rew)
-        ep_len = torch.empty((steps, B), dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        return {"obs": torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev),
+                "act": torch.empty((steps, B), dtype=torch.long, device=dev), "rew": torch.empty((steps, B), **f32),
+                "val": torch.empty((steps, B), **f32), "logp": torch.empty((steps, B), **f32),
+                "done": torch.empty((steps, B), **f32), "ep_ret": torch.empty((steps, B), **f32),
+                "ep_len": torch.empty((steps, B), dtype=torch.int32, device=dev), "last_val": torch.empty(B, **f32)}
+
+    def _rollout_body(self, env, policy, params, steps, buf):
+        obs = buf["obs"]
         env.reset(out_obs=obs[0])
         for t in range(steps):
             a, lp, v = self._act(policy, params, obs[t])
             _, r, te, tr, info = env.step(a, out_obs=obs[t + 1])
-            act[t], logp[t], val[t], rew[t] = a, lp, v, r
-            done[t] = (te | tr).float()
-            ep_ret[t], ep_len[t] = info["episode_return"], info["episode_length"]
-        last_val = self._act(policy, params, obs[steps])[2]
-        ended = ep_len > 0
-        return {"obs": obs[:steps], "act": act, "rew": rew, "val": val, "logp": logp, "done": done,
-                "last_val": last_val, "ep_lens": ep_len[ended].tolist(), "ep_rews": ep_ret[ended].tolist()}
+            buf["act"][t].copy_(a); buf["logp"][t].copy_(lp); buf["val"][t].copy_(v); buf["rew"][t].copy_(r)
+            buf["done"][t].copy_(te | tr)
+            buf["ep_ret"][t].copy_(info["episode_return"]); buf["ep_len"][t].copy_(info["episode_length"])
+        buf["last_val"].copy_(self._act(policy, params, obs[steps])[2])
+
+    @staticmethod
+    def _rollout_result(buf, steps):
+        ended = buf["ep_len"] > 0
+        return {"obs": buf["obs"][:steps], "act": buf["act"], "rew": buf["rew"], "val": buf["val"], "logp": buf["logp"],
+                "done": buf["done"], "last_val": buf["last_val"], "ep_lens": buf["ep_len"][ended].tolist(),
+                "ep_rews": buf["ep_ret"][ended].tolist()}
+
+    def _collect_graphed(self, env, steps, params):
+        """The whole k-step rollout (policy forward, sampling, env step, stores) replayed from one CUDA graph per
+        (env, steps, shared | per-task weights).  Per-task weights are copied into the graph's static stacked tensors
+        before each replay; the meta-policy's own parameters are updated in place by the optimiser, so a graph over
+        them stays valid.  The returned tensors are the graph's buffers: valid until the next rollout of that kind."""
+        key = (id(env), steps, params is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            buf = self._rollout_buffers(env, steps)
+            static = None if params is None else {n: torch.empty_like(p) for n, p in params.items()}
+            if static is not None:
+                for n in static:
+                    static[n].copy_(params[n])
+            side = torch.cuda.Stream(env.device)
+            side.wait_stream(torch.cuda.current_stream(env.device))
+            with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
+                self._act(self.meta_policy, static, buf["obs"][0])
+            torch.cuda.current_stream(env.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._rollout_body(env, self.meta_policy, static, steps, buf)
+            g = self._graphs[key] = (graph, buf, static)
+        graph, buf, static = g
+        if static is not None:
+            for n in static:
+                static[n].copy_(params[n])
+        graph.replay()
+        return self._rollout_result(buf, steps)
 
     def _act(self, policy, params, obs):
         """Sampled action, its log-probability and the value for one frame per task."""

@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--layouts", type=int, default=65536)
     ap.add_argument("--eval-tasks", type=int, default=100)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="rgb",
+    ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="symbolic",
                     help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
     ap.add_argument("--cpu-baseline", action="store_true",
                     help="also time one reference-style PPO iteration (N=1, 2048 steps) on the host cores (oracle port)")
