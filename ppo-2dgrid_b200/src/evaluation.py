@@ -19,8 +19,9 @@ from merlin_b200 import layouts as _layouts
 
 @torch.no_grad()
 def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=None, deterministic=True, poll=64,
-                   env=None):
-    """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)])."""
+                   env=None, act_fn=None):
+    """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)]).
+    `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` replaces `policy.act` (e.g. per-task adapted weights)."""
     seeds = [int(s) for s in seeds]
     B = len(seeds)
     cells, agent = _layouts.generate(difficulty, size, seeds)
@@ -38,8 +39,11 @@ def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=Non
     obs, _ = env.reset()
     was_training = policy.training
     policy.eval()
+    if act_fn is None:
+        def act_fn(o):
+            return policy.act(o, deterministic=deterministic)[0]
     for t in range(env.max_steps):
-        action = policy.act(obs, deterministic=deterministic)[0]
+        action = act_fn(obs)
         obs, _, term, _, info = env.step(action)
         first = (info["episode_length"] > 0) & ~finished
         ret = torch.where(first, info["episode_return"], ret)

@@ -240,6 +240,42 @@ class FOMAML:
         o = obs.transpose(0, 1)  # [B, k, 56, 56, 3]
         return o if self.use_cnn else o.reshape(o.shape[0], o.shape[1], -1)
 
+    @staticmethod
+    def _inner_step(fast, per_task_loss, names, lr):
+        """One SGD step per task on stacked weights, each task's gradient clipped to norm 0.5 (src/fomaml.py:179-182)."""
+        g = torch.autograd.grad(per_task_loss.sum(), [fast[n] for n in names])
+        coef = _clip_coef(g, 0.5)
+        B = coef.shape[0]
+        with torch.no_grad():
+            return {n: (fast[n] - lr * gi * coef.view((B,) + (1,) * (gi.dim() - 1))).requires_grad_(True)
+                    for n, gi in zip(names, g)}
+
+    # ---- few-shot evaluation ------------------------------------------------------------------------------
+    def few_shot_evaluate(self, task_seeds, k_support=256, adapt_steps=1, lr_inner=None):
+        """Adapt-then-evaluate for many tasks at once (batched core of `evaluate_few_shot`,
+        src/distribution_over_tasks.py:132-209, and fomaml/analyze_fomaml_distribution.py:54-86): every task starts
+        from the meta weights, takes `adapt_steps` inner SGD steps, each on a fresh `k_support`-step rollout of its own
+        layout under its current weights, then plays one greedy episode.
+        Returns (returns f64[B], lengths i64[B], reached_goal bool[B]) in the order of `task_seeds`."""
+        from .evaluation import evaluate_seeds
+        seeds = [int(s) for s in task_seeds]
+        meta = self.meta_policy
+        names = [n for n, _ in meta.named_parameters()]
+        lr = self.lr_inner if lr_inner is None else lr_inner
+        env = self._task_env(seeds)
+        fast = _stack(meta, len(seeds))
+        for _ in range(adapt_steps):
+            support = self.collect_trajectory(env, meta, steps=k_support, params=fast)
+            loss, _ = self.compute_loss(support, meta, params=fast)
+            fast = self._inner_step(fast, loss, names, lr)
+
+        def greedy(obs):
+            logits, _ = vmap(lambda p, o: _logits_value(meta, p, o.unsqueeze(0)))(fast, self._fmt(obs))
+            return logits.squeeze(1).argmax(-1)
+
+        with torch.no_grad():
+            return evaluate_seeds(meta, self.sc_difficulty(), self.size, seeds, device=env.device, env=env, act_fn=greedy)
+
     # ---- meta step ----------------------------------------------------------------------------------------
     def meta_train_step(self, task_seeds, k_support=50, k_query=50):
         task_seeds = list(task_seeds)
@@ -257,14 +293,9 @@ class FOMAML:
             env = self._task_env(my_seeds)
             # inner loop: support rollout under the shared meta weights, one SGD step per task
             support = self.collect_trajectory(env, meta, steps=k_support)
-            fast = {n: p.detach().unsqueeze(0).repeat((B,) + (1,) * p.dim()).requires_grad_(True)
-                    for n, p in meta.named_parameters()}
+            fast = _stack(meta, B)
             s_loss, _ = self.compute_loss(support, meta, params=fast)
-            g = torch.autograd.grad(s_loss.sum(), [fast[n] for n in names])
-            coef = _clip_coef(g, 0.5)
-            with torch.no_grad():
-                fast = {n: (fast[n] - self.lr_inner * gi * coef.view((B,) + (1,) * (gi.dim() - 1))).requires_grad_(True)
-                        for n, gi in zip(names, g)}
+            fast = self._inner_step(fast, s_loss, names, self.lr_inner)
             # outer loop: query rollout under each task's adapted weights, first-order gradient
             query = self.collect_trajectory(env, meta, steps=k_query, params=fast)
             lens, rews = query["ep_lens"], query["ep_rews"]
@@ -295,6 +326,12 @@ class FOMAML:
         else:
             avg_rew, avg_steps = 0.0, float(k_query)
         return avg_loss, avg_rew, avg_steps, query_stats
+
+
+def _stack(policy, B):
+    """The module's parameters repeated B times along a new leading axis: one independent copy per task."""
+    return {n: p.detach().unsqueeze(0).repeat((B,) + (1,) * p.dim()).requires_grad_(True)
+            for n, p in policy.named_parameters()}
 
 
 def _logits_value(policy, params, obs):

@@ -68,4 +68,7 @@ int hm_step(int N, int W, int H, int max_steps, int cell_stride, int n_actions, 
   return 0;
 }
 
+// Grid.process_vis on a 49-bit transparency mask (bit vj*7 + vi), for the property tests.
+unsigned long long hm_visibility(unsigned long long transp) { return merlin::visibility(transp); }
+
 }  // extern "C"

@@ -320,3 +320,19 @@ def test_batched_evaluation_matches_sequential_reference_loop():
             steps += 1
             done = te or tr
         assert steps == int(length[k]) and abs(total - ret[k]) < 1e-6 and bool(goal[k]) == bool(te), (s, steps, length[k])
+
+
+def test_fomaml_few_shot_evaluation_batched():
+    """adapt_steps = 0 is zero-shot evaluation of the meta weights; with adaptation every task gets its own weights."""
+    from src.evaluation import evaluate_seeds
+    from src.fomaml import FOMAML
+    torch.manual_seed(4)
+    fo = FOMAML(_sc(), lr_inner=0.05, device="cuda:0", difficulty="medium")
+    seeds = [300000, 300001, 300002, 300003, 300004, 300005]
+    r0, n0, g0 = fo.few_shot_evaluate(seeds, k_support=32, adapt_steps=0)
+    r1, n1, g1 = evaluate_seeds(fo.meta_policy, "medium", 16, seeds, device="cuda:0")
+    assert np.array_equal(n0, n1) and np.allclose(r0, r1) and np.array_equal(g0, g1)
+    before = [p.detach().clone() for p in fo.meta_policy.parameters()]
+    r2, n2, g2 = fo.few_shot_evaluate(seeds, k_support=32, adapt_steps=2)
+    assert r2.shape == (6,) and np.all(n2 >= 1) and np.all(n2 <= 1024) and np.all((r2 > 0) == g2)
+    assert all(torch.equal(a, b) for a, b in zip(before, fo.meta_policy.parameters()))  # the meta weights are untouched

@@ -382,3 +382,41 @@ def test_render_from_symbolic_is_bit_identical_to_step_frames(n_actions):
     with pytest.raises(ValueError):
         env.render(sym_store.float())
     assert env.render(sym_store[:0]).shape == (0, 56, 56, 3)
+
+
+@pytest.mark.parametrize("N", [1, 33, 257, 5000, 9473])
+def test_outputs_stay_inside_their_buffers(N):
+    """Guard bands around every caller-owned output (compute-sanitizer is not available on the GPU pool): frames,
+    symbolic rows and per-env scalars of a ragged batch are written, the bytes before and after them are not."""
+    _, codes, _, layouts, _ = _mods()
+    cells, agent = layouts.generate("mediumhard", 16, range(40))
+    env = _make_gpu_env(N, codes.unpack_to_encoding(cells, 16, 16), agent, max_steps=7)
+    G = 4096  # guard bytes on each side (multiple of 16: the frame pointer must stay 16-byte aligned)
+    dev = "cuda:0"
+
+    def guarded(nbytes):
+        buf = torch.full((G + nbytes + G,), 0xA5, dtype=torch.uint8, device=dev)
+        return buf, buf[G:G + nbytes]
+
+    rgb_all, rgb = guarded(N * 56 * 56 * 3)
+    sym_all, sym = guarded(N * 147 + (-N * 147) % 16)
+    bufs = env.make_step_buffers()
+    raw = {}
+    for name, width in (("reward", 4), ("terminated", 1), ("truncated", 1), ("episode_return", 4), ("episode_length", 4),
+                        ("stuck", 1)):
+        whole, inner = guarded(N * width + (-N * width) % 16)
+        raw[name] = whole
+        t = getattr(bufs, name)
+        setattr(bufs, name, inner[: N * width].view(t.dtype))
+    from merlin_b200 import _lib
+    bufs._extras = _lib.StepExtras(bufs.episode_return.data_ptr(), bufs.episode_length.data_ptr(), bufs.stuck.data_ptr())
+    rgb_v, sym_v = rgb.view(N, 56, 56, 3), sym[: N * 147].view(N, 7, 7, 3)
+    env.reset(out_obs=rgb_v, out_symbolic=sym_v)
+    rng = np.random.default_rng(N)
+    for _ in range(14):  # max_steps 7: the last step ends every env's second episode (unless it reached the goal early)
+        env.step(torch.as_tensor(rng.integers(0, 3, N), device=dev), out_obs=rgb_v, out_symbolic=sym_v, out=bufs)
+    torch.cuda.synchronize()
+    for whole in [rgb_all, sym_all] + list(raw.values()):
+        assert bool((whole[:G] == 0xA5).all()) and bool((whole[-G:] == 0xA5).all())
+    assert bool((sym_all[G + N * 147: G + sym.numel()] == 0xA5).all())  # padding after the last symbolic row
+    assert 0 < int(bufs.episode_length.max()) <= 7 and not bool((rgb_v == 0xA5).all(dim=(1, 2, 3)).any())

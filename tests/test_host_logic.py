@@ -192,3 +192,76 @@ def test_visibility_bitmask_exhaustive_rows():
         rgb, sym, *_ = hm.call(a, do_step=True)
         assert np.array_equal(sym, info["obs_symbolic"])
         assert np.array_equal(rgb, rgb0)
+
+
+# ---- property tests (hypothesis): arbitrary W x H rooms, full object set, arbitrary action strings ----------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_OBJS = [(2, 5, 0), (8, 1, 0), (9, 0, 0), (3, 2, 0), (4, 4, 0), (4, 4, 1), (4, 4, 2), (5, 4, 0), (6, 0, 0), (7, 3, 0),
+         (4, 2, 1), (5, 2, 0), (5, 4, 0)]
+
+
+@st.composite
+def _rooms(draw):
+    W, H = draw(st.integers(3, 14)), draw(st.integers(3, 14))
+    enc = np.zeros((1, W, H, 3), np.uint8)
+    enc[..., 0] = 1
+    enc[:, 0, :, :] = enc[:, -1, :, :] = enc[:, :, 0, :] = enc[:, :, -1, :] = (2, 5, 0)
+    interior = [(x, y) for x in range(1, W - 1) for y in range(1, H - 1)]
+    ax, ay = draw(st.sampled_from(interior))
+    n_obj = draw(st.integers(0, min(12, len(interior) - 1)))
+    for _ in range(n_obj):
+        x, y = draw(st.sampled_from(interior))
+        if (x, y) != (ax, ay):
+            enc[0, x, y] = draw(st.sampled_from(_OBJS))
+    agent = np.array([[ax, ay, draw(st.integers(0, 3))]], np.int32)
+    seven = draw(st.booleans())
+    actions = draw(st.lists(st.integers(0, 6 if seven else 2), min_size=1, max_size=40))
+    return W, H, enc, agent, seven, actions, draw(st.booleans()), draw(st.sampled_from([0.0, 0.03]))
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(_rooms())
+def test_property_kernel_logic_equals_oracle_on_arbitrary_rooms(case):
+    """The kernel's per-env arithmetic (env_logic.cuh, compiled for the host) == the oracle for any room shape,
+    object placement, wrapper setting and action string; frames, symbolic images, rewards, flags and poses bit-exact."""
+    W, H, enc, agent, seven, actions, stuck, bonus = case
+    n_actions = 7 if seven else 3
+    ref = fast.OracleVecEnv(1, enc, agent, max_steps=25, n_actions=n_actions, auto_reset=False, stuck_penalty=stuck,
+                            exploration_bonus=bonus)
+    hm = HostModelEnv(codes.pack_encoding(enc), agent, W, H, 25, n_actions, stuck, bonus)
+    rgb0, sym0 = ref.reset()
+    rgb, sym, *_ = hm.call(np.zeros(1, np.int64), do_step=False)
+    assert np.array_equal(sym, sym0) and np.array_equal(rgb, rgb0)
+    for a in actions:
+        rgb0, r0, te0, tr0, info = ref.step(np.array([a]))
+        rgb, sym, r, te, tr, sk = hm.call(np.array([a]), do_step=True)
+        assert np.array_equal(r, r0) and np.array_equal(te, te0) and np.array_equal(tr, tr0)
+        assert np.array_equal(sk, info["stuck"]) and np.array_equal(sym, info["obs_symbolic"]) and np.array_equal(rgb, rgb0)
+        assert (hm.state[0, 0] & 0xFF, (hm.state[0, 0] >> 8) & 0xFF, (hm.state[0, 0] >> 16) & 3) == (ref.ax[0], ref.ay[0], ref.adir[0])
+        if te0[0] or tr0[0]:
+            break
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, (1 << 49) - 1))
+def test_property_visibility_invariants(transp):
+    """process_vis invariants on any 49-bit transparency pattern: the agent cell is always visible, the row in front of
+    it is reachable only through transparent cells, visibility is monotone in transparency, and an all-opaque row
+    hides everything behind it."""
+    lib = _host_model()
+    lib.hm_visibility.restype = ctypes.c_uint64
+    lib.hm_visibility.argtypes = [ctypes.c_uint64]
+    vis = lib.hm_visibility(transp)
+    agent_bit = 1 << (6 * 7 + 3)
+    assert vis & agent_bit
+    more = lib.hm_visibility(transp | (1 << 20) | (1 << 45))
+    assert more & vis == vis  # monotone: making cells transparent never hides anything
+    for row in range(6):  # rows are vj = 0 (far) .. 6 (agent row)
+        if (transp >> (row * 7)) & 0x7F == 0 and row < 6:
+            hidden_above = (1 << (row * 7)) - 1
+            lit_row = (vis >> (row * 7)) & 0x7F
+            if lit_row == 0:
+                assert vis & hidden_above == 0
+    if not (transp & agent_bit):  # the agent stands on an opaque cell (closed door): it sees only its own cell
+        assert vis == agent_bit
