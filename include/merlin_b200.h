@@ -9,6 +9,7 @@
  *                                 src/custom_envs/base_env.py:32-41 (max_steps = 4*size^2, view 7)
  *   merlin_env_upload_layouts     the result of MiniGridEnv.reset() -> _gen_grid()
  *                                 src/custom_envs/medium_hard_env.py:12-45 (and the four siblings)
+ *   merlin_env_generate_layouts   the same `_gen_grid` routines run on the device (fresh layouts without a host pool)
  *   merlin_env_set_tile_atlas     Grid.render_tile cache used by RGBImgPartialObsWrapper
  *                                 (src/scenario_creator/scenario_creator.py:48, tile_size 8)
  *   merlin_env_reset              env.reset()   src/ppo.py:35,65,96 ; src/fomaml.py:63,92,184
@@ -86,6 +87,22 @@ int merlin_env_destroy(merlin_env_t* h);
 
 /* HOST inputs. cells: [n_layouts][H*W] packed codes; agent_xyd: [n_layouts][3] = x, y, dir. Replaces the pool. */
 int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32_t* agent_xyd, int32_t n_layouts);
+/* Generate the pool ON THE DEVICE: n_layouts layouts of `difficulty` (the reference's `_gen_grid` routines,
+ * src/custom_envs/{easy,medium,medium_hard,hard,hardest}_env.py, same algorithm and distributions) from a counter-based
+ * generator keyed by (seed, first_number + slot).  NOT the layouts numpy's PCG64 stream would give for a reference seed:
+ * use merlin_env_upload_layouts with host-generated layouts to reproduce `env.reset(seed=s)`.  Replaces the pool (in
+ * place when n_layouts is unchanged), resets the cursors.  Synchronous. */
+#define MERLIN_D_EASY 0
+#define MERLIN_D_MEDIUM 1
+#define MERLIN_D_MEDIUMHARD 2
+#define MERLIN_D_HARD 3
+#define MERLIN_D_HARDEST 4
+int merlin_env_generate_layouts(merlin_env_t* h, int32_t difficulty, uint64_t seed, int64_t first_number,
+                                int32_t n_layouts, void* stream);
+/* Synchronous copy of the current pool to HOST buffers (either may be NULL): cells u8[n_layouts][H*W], agent_xyd
+ * i32[n_layouts][3]; merlin_env_layout_count gives n_layouts. */
+int merlin_env_read_layouts(merlin_env_t* h, uint8_t* cells, int32_t* agent_xyd);
+int merlin_env_layout_count(merlin_env_t* h);
 /* HOST input. tiles: [128][tile*tile*3] u8, indexed by packed code (0 = unseen cell, 10 = agent on empty,
  * 13/14/15 | colour<<4 = agent carrying key/ball/box). Required before an RGB observation is requested. */
 int merlin_env_set_tile_atlas(merlin_env_t* h, const uint8_t* tiles, int32_t n_tiles);

@@ -216,6 +216,65 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
   return merlin_env_set_cursors(h, nullptr);
 }
 
+int merlin_env_generate_layouts(merlin_env_t* h, int32_t difficulty, uint64_t seed, int64_t first_number,
+                                int32_t n_layouts, void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (difficulty < MERLIN_D_EASY || difficulty > MERLIN_D_HARDEST) return fail(MERLIN_EINVAL, "unknown difficulty id");
+  if (n_layouts < 1 || first_number < 0) return fail(MERLIN_EINVAL, "merlin_env_generate_layouts: bad count / first_number");
+  const int W = h->cfg.width, H = h->cfg.height;
+  const int min_side = difficulty == MERLIN_D_HARDEST ? 8 : (difficulty == MERLIN_D_EASY ? 6 : 4);
+  if (W < min_side || H < min_side) return fail(MERLIN_EINVAL, "grid too small for this difficulty's layout routine");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaDeviceSynchronize();  // nothing may still be reading the old pool
+  if (err != cudaSuccess) return cuda_fail(err, "layout generation (sync)");
+  if (n_layouts != h->n_layouts) {
+    uint8_t* d_cells = nullptr;
+    uint32_t* d_agent = nullptr;
+    if (cudaMalloc(&d_cells, (size_t)n_layouts * h->cell_stride) != cudaSuccess ||
+        cudaMalloc(&d_agent, (size_t)n_layouts * sizeof(uint32_t)) != cudaSuccess) {
+      cudaFree(d_cells);
+      return cuda_fail(cudaGetLastError(), "layout pool allocation");
+    }
+    cudaFree(h->pool_cells); cudaFree(h->pool_agent);
+    h->pool_cells = d_cells; h->pool_agent = d_agent; h->n_layouts = n_layouts;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  err = launch_layouts(h->pool_cells, h->pool_agent, h->cell_stride, W, H, difficulty, seed, first_number, 0, n_layouts,
+                       h->sm_count, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  if (err != cudaSuccess) return cuda_fail(err, "layout generation");
+  uint32_t present[4] = {(1u << KIND_UNSEEN) | (1u << CODE_EMPTY) | (1u << KIND_AGENT), 0, 0, 0};
+  const uint32_t goal = T_GOAL | (1u << 4);
+  present[CODE_WALL >> 5] |= 1u << (CODE_WALL & 31);
+  present[goal >> 5] |= 1u << (goal & 31);
+  if (h->mutable_grid) present[0] = present[1] = present[2] = present[3] = 0xffffffffu;
+  err = cudaMemcpy(h->tile_present, present, sizeof present, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cuda_fail(err, "layout generation (mask)");
+  h->launches += 1;
+  h->was_reset = false;
+  return merlin_env_set_cursors(h, nullptr);
+}
+
+int merlin_env_read_layouts(merlin_env_t* h, uint8_t* cells, int32_t* agent_xyd) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (h->n_layouts < 1) return fail(MERLIN_ESTATE, "no layout pool");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaDeviceSynchronize();
+  const size_t HW = (size_t)h->cfg.width * h->cfg.height, L = (size_t)h->n_layouts;
+  if (err == cudaSuccess && cells) err = cudaMemcpy2D(cells, HW, h->pool_cells, h->cell_stride, HW, L, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && agent_xyd) {
+    std::vector<uint32_t> a(L);
+    err = cudaMemcpy(a.data(), h->pool_agent, L * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    for (size_t l = 0; l < L && err == cudaSuccess; ++l) {
+      agent_xyd[3 * l] = a[l] & 0xff; agent_xyd[3 * l + 1] = (a[l] >> 8) & 0xff; agent_xyd[3 * l + 2] = (a[l] >> 16) & 3;
+    }
+  }
+  if (err != cudaSuccess) return cuda_fail(err, "layout read-back");
+  return MERLIN_OK;
+}
+
+int merlin_env_layout_count(merlin_env_t* h) { return h ? h->n_layouts : 0; }
+
 int merlin_env_set_tile_atlas(merlin_env_t* h, const uint8_t* tiles, int32_t n_tiles) {
   if (!h || !tiles || n_tiles != kAtlasTiles) return fail(MERLIN_EINVAL, "atlas must hold exactly 128 tiles of 8x8x3");
   DeviceGuard guard(h->cfg.device);

@@ -72,6 +72,11 @@ struct RenderParams {
   long long n_rows;          // rows of `sym` (index bound), 0 = unchecked
 };
 cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream);
+// On-device layout generation (layout_kernels.cu): fills pool slots first_slot .. first_slot+count-1 with layouts number
+// first_number .. of the stream `seed`; difficulty 0 easy, 1 medium, 2 mediumhard, 3 hard, 4 hardest.
+cudaError_t launch_layouts(uint8_t* pool_cells, uint32_t* pool_agent, int cell_stride, int W, int H, int difficulty,
+                           uint64_t seed, long long first_number, int first_slot, int count, int sm_count,
+                           cudaStream_t stream);
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream);
 

@@ -17,6 +17,7 @@ F_AUTO_RESET, F_RESET_SAME, F_SEVEN_ACTIONS, F_STUCK_PENALTY, F_EXPLORE_BONUS = 
 
 EXPORTS = (
     "merlin_env_default_config", "merlin_env_create", "merlin_env_destroy", "merlin_env_upload_layouts",
+    "merlin_env_generate_layouts", "merlin_env_read_layouts", "merlin_env_layout_count",
     "merlin_env_set_tile_atlas", "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step",
     "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
     "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_env_render", "merlin_gae",
@@ -54,6 +55,9 @@ def load():
     lib.merlin_env_create.argtypes = [C.POINTER(EnvConfig), C.POINTER(vp)]
     lib.merlin_env_destroy.argtypes = [vp]
     lib.merlin_env_upload_layouts.argtypes = [vp, vp, vp, i32]
+    lib.merlin_env_generate_layouts.argtypes = [vp, i32, C.c_uint64, i64, i32, vp]
+    lib.merlin_env_read_layouts.argtypes = [vp, vp, vp]
+    lib.merlin_env_layout_count.argtypes = [vp]
     lib.merlin_env_set_tile_atlas.argtypes = [vp, vp, i32]
     lib.merlin_env_set_cursors.argtypes = [vp, vp]
     lib.merlin_env_reset.argtypes = [vp, vp, vp, vp, vp]
@@ -75,6 +79,7 @@ def load():
     lib.merlin_last_error.restype = C.c_char_p
     lib.merlin_version.restype = C.c_char_p
     for name in ("merlin_env_create", "merlin_env_destroy", "merlin_env_upload_layouts", "merlin_env_set_tile_atlas",
+                 "merlin_env_generate_layouts", "merlin_env_read_layouts", "merlin_env_layout_count",
                  "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step", "merlin_env_state_ptrs",
                  "merlin_env_read_state", "merlin_env_bad_actions", "merlin_gae"):
         getattr(lib, name).restype = C.c_int

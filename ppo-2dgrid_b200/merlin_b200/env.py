@@ -40,7 +40,7 @@ class BatchedMerlinEnv:
     def __init__(self, num_envs, cells=None, agent=None, *, enc=None, width=None, height=None, max_steps=None,
                  device="cuda", n_actions=3, auto_reset=True, reset_mode="next", stuck_penalty=False,
                  stuck_max_stay=3, stuck_penalty_value=-0.1, exploration_bonus=0.0, want_symbolic=True,
-                 want_rgb=True):
+                 want_rgb=True, generate=None):
         """cells: packed u8[L, H*W] (merlin_b200.codes) or `enc`: Grid.encode() arrays u8[L, W, H, 3];
         agent: i32[L, 3] = (x, y, dir).  `reset_mode`: "next" advances each env's pool cursor by num_envs at
         every restart (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
@@ -57,11 +57,15 @@ class BatchedMerlinEnv:
             enc = np.asarray(enc)
             width, height = enc.shape[1], enc.shape[2]
             cells = codes.pack_encoding(enc)
-        if cells is None or agent is None:
-            raise ValueError("a layout pool (cells or enc, and agent) is required")
-        cells = np.ascontiguousarray(cells, dtype=np.uint8)
-        if width is None:
-            width = height = int(round(cells.shape[1] ** 0.5))
+        if generate is not None:
+            if width is None:
+                raise ValueError("width/height are required with generate=(difficulty, seed, n_layouts)")
+        elif cells is None or agent is None:
+            raise ValueError("a layout pool (cells or enc, and agent) or generate=(difficulty, seed, n_layouts) is required")
+        else:
+            cells = np.ascontiguousarray(cells, dtype=np.uint8)
+            if width is None:
+                width = height = int(round(cells.shape[1] ** 0.5))
         self.num_envs, self.width, self.height = int(num_envs), int(width), int(height)
         self.n_actions = n_actions
         self.want_symbolic, self.want_rgb = want_symbolic, want_rgb
@@ -88,7 +92,10 @@ class BatchedMerlinEnv:
         if want_rgb:
             atlas = np.ascontiguousarray(tiles.build_atlas(TILE))
             _lib.check(self._lib.merlin_env_set_tile_atlas(self._h, atlas.ctypes.data, atlas.shape[0]))
-        self.upload_layouts(cells, agent)
+        if generate is not None:
+            self.generate_layouts(*generate)
+        else:
+            self.upload_layouts(cells, agent)
 
         N, dev = self.num_envs, self.device
         self.obs = torch.empty((N,) + OBS_SHAPE, dtype=torch.uint8, device=dev) if want_rgb else None
@@ -117,6 +124,27 @@ class BatchedMerlinEnv:
         _lib.check(self._lib.merlin_env_upload_layouts(self._h, cells.ctypes.data, agent.ctypes.data, cells.shape[0]))
         self.n_layouts = cells.shape[0]
         self._pool_cells_host = cells
+
+    DIFFICULTY_IDS = {"easy": 0, "medium": 1, "mediumhard": 2, "hard": 3, "hardest": 4}
+
+    def generate_layouts(self, difficulty, seed, n_layouts, first_number=0):
+        """Fill the pool on the device with `n_layouts` fresh layouts of `difficulty` (layouts number first_number..
+        of the stream `seed`; same generators and distributions as merlin_b200.layouts, different random stream --
+        not the reference's `reset(seed=s)` layouts).  Resets the cursors; call `reset()` afterwards."""
+        if difficulty not in self.DIFFICULTY_IDS:
+            raise ValueError(f"Unknown difficulty: {difficulty}")
+        _lib.check(self._lib.merlin_env_generate_layouts(self._h, self.DIFFICULTY_IDS[difficulty], int(seed) & (2**64 - 1),
+                                                         int(first_number), int(n_layouts), self._stream()))
+        self.n_layouts = int(n_layouts)
+        self._pool_cells_host = None
+
+    def layouts_numpy(self):
+        """Host copy of the current pool: (cells u8[L, H*W], agent i32[L, 3])."""
+        L = int(self._lib.merlin_env_layout_count(self._h))
+        cells = np.empty((L, self.width * self.height), dtype=np.uint8)
+        agent = np.empty((L, 3), dtype=np.int32)
+        _lib.check(self._lib.merlin_env_read_layouts(self._h, cells.ctypes.data, agent.ctypes.data))
+        return cells, agent
 
     def set_cursors(self, cursor=None):
         """cursor[e] = pool index env e loads at its next (full) reset; None = e % n_layouts."""
@@ -211,6 +239,8 @@ class BatchedMerlinEnv:
     def cells_numpy(self):
         """Host copy of every env's current grid as packed cells [N, H*W]."""
         if self.n_actions == 3:  # immutable grids: envs read the pool in place
+            if self._pool_cells_host is None:
+                self._pool_cells_host = self.layouts_numpy()[0]
             return self._pool_cells_host[self.state_numpy()["layout"]]
         out = np.empty((self.num_envs, self.width * self.height), dtype=np.uint8)
         _lib.check(self._lib.merlin_env_read_state(self._h, None, out.ctypes.data, None))

@@ -69,9 +69,11 @@ class ScenarioCreator:
     # ---- batched surface (additive) ---------------------------------------------------------------------
     def create_batched_env(self, difficulty="easy", num_envs=1, device="cuda", layouts=None, seeds=None,
                            stuck_penalty=False, exploration_bonus=0.0, fomaml_mode=False, size=None,
-                           want_symbolic=False, **env_kwargs):
+                           want_symbolic=False, n_layouts=None, **env_kwargs):
         """N envs of `difficulty` on `device`.  Layout pool: `layouts=(cells u8[L, H*W], agent i32[L, 3])`, or
         generated on the host from `seeds` (one `reset(seed=s)` layout per seed; default: seeds 0..max(N, 1024)-1).
+        `layouts="device"`: the pool (`n_layouts` entries, default max(N, 1024)) is generated on the GPU from the integer
+        `seeds` -- fresh layouts of the right distribution, not the reference's per-seed layouts.
         `fomaml_mode`: finished envs restart on their own layout (src/fomaml.py:92) instead of the next one."""
         from merlin_b200 import BatchedMerlinEnv
         from merlin_b200 import layouts as _layouts
@@ -80,12 +82,20 @@ class ScenarioCreator:
         params = {**self.global_cfg, **cfg.get("params", {})}
         size = int(size if size is not None else params.get("size", 16))
         diff = _register.DIFFICULTY_OF[cfg["env_id"]]
-        if layouts is None:
-            if seeds is None:
-                seeds = range(max(int(num_envs), 1024))
-            layouts = _layouts.generate(diff, size, seeds)
-        cells, agent = layouts
-        env = BatchedMerlinEnv(int(num_envs), np.asarray(cells), np.asarray(agent), width=size, height=size,
+        common = dict(width=size, height=size)
+        if isinstance(layouts, str):
+            if layouts != "device":
+                raise ValueError("layouts must be (cells, agent), None (host-generated from seeds) or 'device'")
+            pool = dict(generate=(diff, int(seeds or 0), int(n_layouts or max(int(num_envs), 1024))))
+            cells = agent = None
+        else:
+            if layouts is None:
+                if seeds is None:
+                    seeds = range(int(n_layouts or max(int(num_envs), 1024)))
+                layouts = _layouts.generate(diff, size, seeds)
+            cells, agent = (np.asarray(a) for a in layouts)
+            pool = {}
+        env = BatchedMerlinEnv(int(num_envs), cells, agent, **common, **pool,
                                max_steps=env_kwargs.pop("max_steps", params.get("max_steps")), device=device,
                                reset_mode="same" if fomaml_mode else "next", stuck_penalty=stuck_penalty,
                                exploration_bonus=exploration_bonus, want_symbolic=want_symbolic, **env_kwargs)

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--seed", type=int, default=777)
     ap.add_argument("--layouts", type=int, default=65536)
     ap.add_argument("--eval-tasks", type=int, default=100)
+    ap.add_argument("--device-layouts", action="store_true",
+                    help="generate the layout pool on the GPU (fresh layouts, not the reference's per-seed ones)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="symbolic",
                     help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
@@ -70,15 +72,20 @@ def main():
     t_lay = time.perf_counter()
     per_rank = a.layouts // world
     base = a.seed * 1_000_000 + rank * per_rank
-    from multiprocessing import Pool
-    chunks = [range(base + i, min(base + i + 2048, base + per_rank)) for i in range(0, per_rank, 2048)]
-    with Pool(min(len(chunks), len(os.sched_getaffinity(0)))) as pool:
-        parts = pool.starmap(layouts.generate, [(a.difficulty, 16, c) for c in chunks])
-    cells = np.concatenate([p[0] for p in parts])
-    agent_xyd = np.concatenate([p[1] for p in parts])
+    if a.device_layouts:
+        env = sc.create_batched_env(a.difficulty, a.envs, device=dev, layouts="device", seeds=a.seed * 1000 + rank,
+                                    n_layouts=per_rank, want_symbolic=a.obs_storage == "symbolic")
+        torch.cuda.synchronize(dev)
+    else:
+        from multiprocessing import Pool
+        chunks = [range(base + i, min(base + i + 2048, base + per_rank)) for i in range(0, per_rank, 2048)]
+        with Pool(min(len(chunks), len(os.sched_getaffinity(0)))) as pool:
+            parts = pool.starmap(layouts.generate, [(a.difficulty, 16, c) for c in chunks])
+        cells = np.concatenate([p[0] for p in parts])
+        agent_xyd = np.concatenate([p[1] for p in parts])
+        env = sc.create_batched_env(a.difficulty, a.envs, device=dev, layouts=(cells, agent_xyd),
+                                    want_symbolic=a.obs_storage == "symbolic")
     t_lay = time.perf_counter() - t_lay
-    env = sc.create_batched_env(a.difficulty, a.envs, device=dev, layouts=(cells, agent_xyd),
-                                want_symbolic=a.obs_storage == "symbolic")
     agent = PPO(env, lr=a.lr, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=a.update_epochs,
                 batch_size=a.envs * a.horizon, minibatch_size=a.minibatch, vf_coef=0.5, ent_coef=a.ent_coef,
                 use_cuda_graph=not a.no_graph, obs_storage=a.obs_storage)
@@ -128,7 +135,7 @@ def main():
                           "cuda_graph_rollout": not a.no_graph, "obs_storage": a.obs_storage,
                           "rollout_obs_bytes": int(agent.buffer.states.numel() * agent.buffer.states.element_size()),
                           "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "layout_pool_per_gpu": per_rank,
-                          "layout_gen_host_s": t_lay, "dtype": "fp32 policy (PyTorch), u8 frames", "seed": a.seed},
+                          "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch), u8 frames", "seed": a.seed},
                "eval": {"tasks": a.eval_tasks, "seeds": "200000..", "mean_return": float(np.mean(r)),
                         "mean_steps": float(np.mean(n)), "success_rate": float(np.mean(g)), "eval_s": te},
                "train_log": log[:: max(1, len(log) // 20)] + log[-1:]}
