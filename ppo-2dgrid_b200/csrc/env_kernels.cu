@@ -270,8 +270,12 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 // ---------------------------------------------------------------------------------------------------
 // env_kernel_tile<T, STEP>: a CTA owns a tile of T <= 32 consecutive envs; warp 0 runs the state phase, every
 // warp of the CTA takes frames of the tile.  Two CTAs per SM overlap one tile's state phase with another's frames.
-// 256 threads, 2 CTAs per SM (128 registers): measured best on B200; 512-thread CTAs, 3 CTAs/SM at 80 registers, the
-// blit map in shared memory, and overlapping the next tile's state phase with this tile's frames were all slower.
+// 256 threads, 2 CTAs per SM (128 registers): measured best on B200 (0.99 of the HBM copy peak at 1M envs).  Slower,
+// all between 0.69 and 0.94: 512-thread CTAs; 3 CTAs/SM at 80 registers; the blit map in shared memory; overlapping the
+// next tile's state phase with this tile's frames; all 8 warps writing ONE frame at a time (0.91); and splitting the
+// work into a state kernel + a high-occupancy frame-only kernel (0.84 at 24 warps/SM, 0.73 at 40: more concurrent
+// frame streams lower the achieved DRAM write bandwidth).  A plain vectorised fill reaches 7.4 TB/s on this part, so
+// ~14 % of DRAM headroom remains; the fused kernel's L1/LSU pipe is 76 % busy (ncu) and is the co-limit.
 constexpr int kTileThreads = 256;
 __host__ __device__ constexpr int tile_smem_bytes(int T) {
   return kAtlasBytes + ((T * kKindStride + T * kSymBytes + 15) & ~15) + 16;
