@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 // all between 0.69 and 0.94: 512-thread CTAs; 3 CTAs/SM at 80 registers; the blit map in shared memory; overlapping the
 // next tile's state phase with this tile's frames; all 8 warps writing ONE frame at a time (0.91); and splitting the
 // work into a state kernel + a high-occupancy frame-only kernel (0.84 at 24 warps/SM, 0.73 at 40: more concurrent
-// frame streams lower the achieved DRAM write bandwidth).  A plain vectorised fill reaches 7.4 TB/s on this part, so
+// frame streams lower the achieved DRAM write bandwidth); 1 CTA/SM (0.71: nothing overlaps the state phase); 128-thread
+// CTAs x 2 (0.96) or x 4 (0.91); 64-env tiles with two state warps (0.94); 16-env tiles (0.84).  A plain vectorised fill reaches 7.4 TB/s on this part, so
 // ~14 % of DRAM headroom remains; the fused kernel's L1/LSU pipe is 76 % busy (ncu) and is the co-limit.
 constexpr int kTileThreads = 256;
 __host__ __device__ constexpr int tile_smem_bytes(int T) {
