@@ -327,8 +327,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvPara
 //     49-bit mask the visibility routine consumes; every lane then knows the visibility of its own cells.
 constexpr int kWarpKernelThreads = 256;
 
+// The blit map lives in shared memory here (not in 19 registers per lane as in the other kernels): at the batch sizes
+// this kernel serves the run time is launch latency + the dependent-load chain of one env, not the store pipe, and
+// 56 registers let 3+ CTAs per SM hold every env of a <= 16k batch at once (measured: 28.7 vs 31.9 us at 16384 envs).
 template <bool STEP>
-__global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const EnvParams p) {
+__global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -337,10 +340,10 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const E
   uint8_t* atlas_s = smem;
   uint8_t* kp = smem + kAtlasBytes + warp * kWarpKindStride;   // this warp's 49 tile kinds
 
-  uint32_t lut[kChunksPerLane];
+  uint32_t* lut_s = reinterpret_cast<uint32_t*>(smem + kAtlasBytes + (blockDim.x >> 5) * kWarpKindStride);
   if (f.want_rgb) {
     stage_atlas(p, atlas_s);
-    load_lut(p, lane, lut);
+    for (int i = threadIdx.x; i < kChunksPerLane * 32; i += blockDim.x) lut_s[i] = __ldg(p.blit_lut + i);
   }
   __syncthreads();
 
@@ -461,7 +464,21 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 2) env_kernel_warp(const E
       }
     }
     __syncwarp();
-    if (f.want_rgb) blit_frame(atlas_s, kp, lut, p.obs_rgb + (size_t)e * kImgBytes, lane);
+    if (f.want_rgb) {
+      const uint2* atlas64 = reinterpret_cast<const uint2*>(atlas_s);
+      uint8_t* frame = p.obs_rgb + (size_t)e * kImgBytes;
+#pragma unroll 4
+      for (int k = 0; k < kChunksPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (c < kChunks) {
+          const uint32_t q = lut_s[c];
+          const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
+          const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
+          const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];
+          st_stream_v4(frame + c * 16, a.x, a.y, b.x, b.y);
+        }
+      }
+    }
     __syncwarp();  // kp is reused by this warp's next env
   }
 }
@@ -583,7 +600,7 @@ static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStre
 template <bool STEP>
 static cudaError_t launch_warp_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
   constexpr int warps = kWarpKernelThreads / 32;
-  const size_t smem = kAtlasBytes + warps * kWarpKindStride;
+  const size_t smem = kAtlasBytes + warps * kWarpKindStride + kChunksPerLane * 32 * 4;
   static int blocks_per_sm_dev[64] = {};
   int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
   if (!blocks_per_sm) {

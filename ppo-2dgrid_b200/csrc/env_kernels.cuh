@@ -11,7 +11,7 @@ namespace merlin {
 constexpr int kThreads = 256;                 // 8 warps per CTA
 // automatic kernel choice for RGB observations (1 group / 2 warp / 3 tile), from the B200 sweep in profiles/
 #ifndef MERLIN_AUTO_RGB_CHOICE
-#define MERLIN_AUTO_RGB_CHOICE(N, SMS) ((N) <= 8192 ? 2 : 3)
+#define MERLIN_AUTO_RGB_CHOICE(N, SMS) ((N) <= 24576 ? 2 : 3)
 #endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576

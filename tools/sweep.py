@@ -72,15 +72,32 @@ def main():
                 e.record()
             torch.cuda.synchronize()
             ms_cold = sorted(s.elapsed_time(e) for s, e in evs)[k // 2]
+            # 64 steps replayed from one CUDA graph: the kernel without the host's per-call cost (how PPO runs it)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(64):
+                    env.step(acts[i % 16])
+            graph.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(4):
+                graph.replay()
+            g1.record()
+            torch.cuda.synchronize()
+            ms_graph = g0.elapsed_time(g1) / 256
             row = {"envs": N, "mode": mode, "algorithmic_bytes_per_step": algo,
                    "ms_per_launch_back_to_back": ms_b2b, "env_steps_per_s": N / ms_b2b * 1e3,
                    "achieved_gbs": algo * N / ms_b2b / 1e6, "frac_of_hbm_peak": algo * N / ms_b2b / 1e6 / peak,
                    "ms_per_launch_l2_flushed_median": ms_cold, "achieved_gbs_l2_flushed": algo * N / ms_cold / 1e6,
+                   "ms_per_launch_cuda_graph": ms_graph, "env_steps_per_s_cuda_graph": N / ms_graph * 1e3,
                    "working_set_mb": algo * N / 1e6}
             rows.append(row)
             if a.compact:
                 print(f"N={N:8d} {mode:8s} b2b {ms_b2b*1e3:8.1f} us  {row['env_steps_per_s']:.3e}/s  frac {row['frac_of_hbm_peak']:.3f}  "
-                      f"cold {ms_cold*1e3:8.1f} us", flush=True)
+                      f"cold {ms_cold*1e3:8.1f} us  graph {ms_graph*1e3:8.1f} us ({N / ms_graph * 1e3:.3e}/s)", flush=True)
             else:
                 print(json.dumps(row), flush=True)
             env.close()
