@@ -85,7 +85,9 @@ void merlin_env_default_config(merlin_env_config_t* cfg);
 int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out);
 int merlin_env_destroy(merlin_env_t* h);
 
-/* HOST inputs. cells: [n_layouts][H*W] packed codes; agent_xyd: [n_layouts][3] = x, y, dir. Replaces the pool. */
+/* HOST inputs. cells: [n_layouts][H*W] packed codes; agent_xyd: [n_layouts][3] = x, y, dir. Replaces the pool and
+ * resets the cursors (reset() must follow).  A pool of the SAME size is overwritten in place: device addresses, and
+ * CUDA graphs captured over reset/step, stay valid; a different size reallocates and invalidates such graphs. */
 int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32_t* agent_xyd, int32_t n_layouts);
 /* Generate the pool ON THE DEVICE: n_layouts layouts of `difficulty` (the reference's `_gen_grid` routines,
  * src/custom_envs/{easy,medium,medium_hard,hard,hardest}_env.py, same algorithm and distributions) from a counter-based

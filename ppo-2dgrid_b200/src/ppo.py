@@ -57,7 +57,7 @@ class PPO:
             self.ac = MLPActorCritic(self.obs_shape[0], act_dim).to(self.device)
         parallel.broadcast_parameters(self.ac)
         self.optimizer = optim.Adam(self.ac.parameters(), lr=lr)
-        self._grads = FlatOrNone(self.ac) if parallel.world_size() > 1 else None
+        self._grads = parallel.FlatGrads(self.ac.parameters()) if parallel.world_size() > 1 else None
 
         # 'symbolic': the rollout keeps the 147-byte Grid.encode image per step (64x smaller than the frame); minibatches
         # are rendered on read by merlin_env_render, straight into the blocked layout the first conv layer consumes
@@ -78,6 +78,7 @@ class PPO:
             self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
             self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
             self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
+            self._done_tmp = torch.zeros(N, dtype=torch.bool, device=self.device)
         self.use_cuda_graph = bool(use_cuda_graph) and self.batched
         self._graph = None
 
@@ -121,8 +122,6 @@ class PPO:
 
     @torch.no_grad()
     def _collect_batched(self):
-        if not hasattr(self, "_done_tmp"):
-            self._done_tmp = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         if self.use_cuda_graph:
             if self._graph is None:
                 side = torch.cuda.Stream(self.device)
@@ -230,6 +229,3 @@ class PPO:
             self.update(self.collect_rollouts())
             steps_done += self.batch_size * parallel.world_size()
 
-
-def FlatOrNone(module):
-    return parallel.FlatGrads(module.parameters())
