@@ -406,7 +406,7 @@ const char* merlin_env_step_kernel(merlin_env_t* h, int rgb) {
 }
 
 int merlin_set_kernel_choice(int choice) {
-  if (choice < 0 || choice > 3) return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp) or 3 (tile)");
+  if (choice < 0 || choice > 5 || choice == 4) return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile) or 5 (symbolic-only)");
   set_kernel_choice(choice);
   return MERLIN_OK;
 }

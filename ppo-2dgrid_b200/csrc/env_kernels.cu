@@ -320,6 +320,37 @@ __global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvPara
 }
 
 // ---------------------------------------------------------------------------------------------------
+// env_kernel_sym<STEP>: symbolic observations only (no frame phase): one warp per 32 envs, plain grid.  Without the
+// blit map and the frame loop the state phase fits in ~72 registers, so six to seven 128-thread CTAs are resident per
+// SM instead of one 256-thread CTA of env_kernel<32>: this mode is instruction/latency-bound (449 B per env-step), and
+// occupancy is what it needs.
+template <bool STEP>
+__global__ void __launch_bounds__(128) env_kernel_sym(const EnvParams p, const int n_groups) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const Flags f(p);
+  uint8_t* warp_s = smem + warp * warp_smem_bytes(32);
+  uint8_t* kinds_s = warp_s;
+  uint8_t* sym_s = warp_s + 32 * kKindStride;
+  const int g = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= n_groups) return;
+  const int e0 = g * 32;
+  const unsigned render_mask = state_phase<32, STEP>(p, f, e0, lane, kinds_s, sym_s);
+  if (f.want_sym && render_mask)
+    emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(32, p.N - e0), render_mask, lane, 32);
+}
+
+template <bool STEP>
+static cudaError_t launch_sym_kernel(const EnvParams& p, cudaStream_t stream) {
+  constexpr int threads = 128, warps = threads / 32;
+  const int n_groups = (p.N + 31) / 32;
+  const size_t smem = warps * warp_smem_bytes(32);
+  env_kernel_sym<STEP><<<(n_groups + warps - 1) / warps, threads, smem, stream>>>(p, n_groups);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // env_kernel_warp<STEP>: one WARP per environment.
 //   * state / action / forward cell are loaded at warp-uniform addresses (one broadcast transaction each) and the
 //     step logic runs redundantly on all lanes; lane 0 alone writes the per-env outputs and the new state.
@@ -619,11 +650,12 @@ template <bool STEP>
 static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t stream) {
   int choice = g_kernel_choice;
   if (choice == 0) {
-    // symbolic-only observations are instruction-bound: the cheapest state phase, a warp per group of envs
-    if (p.obs_rgb == nullptr) choice = 1;
+    // symbolic-only observations are instruction-bound: the state phase alone, at high occupancy
+    if (p.obs_rgb == nullptr) choice = 5;
     else choice = MERLIN_AUTO_RGB_CHOICE(p.N, sm_count);
   }
   if (choice == 2) return launch_warp_kernel<STEP>(p, sm_count, stream);
+  if (choice == 5) return launch_sym_kernel<STEP>(p, stream);
   if (choice == 3) {
     // tiles of 32 envs once every SM gets a few; smaller tiles spread a small batch over more CTAs
     if (p.N >= sm_count * 2 * 32) return launch_tile_kernel<32, STEP>(p, sm_count, stream);
@@ -640,7 +672,8 @@ static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t s
 
 const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
   int choice = g_kernel_choice;
-  if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 1;
+  if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 5;
+  if (choice == 5) return "merlin::env_kernel_sym<true>";
   if (choice == 2) return "merlin::env_kernel_warp<true>";
   if (choice == 3)
     return n_envs >= sm_count * 64 ? "merlin::env_kernel_tile<32,true>"

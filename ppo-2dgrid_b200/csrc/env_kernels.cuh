@@ -52,7 +52,8 @@ struct EnvParams {
   uint8_t* out_stuck;
 };
 
-// kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile
+// kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile,
+// 5 = env_kernel_sym (state phase only: any RGB output pointer is ignored)
 void set_kernel_choice(int choice);
 const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);

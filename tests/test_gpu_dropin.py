@@ -336,3 +336,35 @@ def test_fomaml_few_shot_evaluation_batched():
     r2, n2, g2 = fo.few_shot_evaluate(seeds, k_support=32, adapt_steps=2)
     assert r2.shape == (6,) and np.all(n2 >= 1) and np.all(n2 <= 1024) and np.all((r2 > 0) == g2)
     assert all(torch.equal(a, b) for a, b in zip(before, fo.meta_policy.parameters()))  # the meta weights are untouched
+
+
+# ---- symbolic-only mode (automatic kernel choice: no frames requested -> state-phase-only kernel) ----------------
+def _to_np(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("N,n_actions", [(1, 3), (37, 3), (5000, 3), (70000, 3), (300, 7)])
+def test_symbolic_only_observations(N, n_actions):
+    """want_rgb=False: the state-phase-only kernel (no frames, no atlas): symbolic images, rewards, flags, poses."""
+    from merlin_b200 import BatchedMerlinEnv, codes, layouts
+    from test_gpu_parity import _object_layouts
+    rng = np.random.default_rng(N)
+    if n_actions == 3:
+        cells, agent = layouts.generate("hard", 16, range(200))
+        enc = codes.unpack_to_encoding(cells, 16, 16)
+    else:
+        enc, agent = _object_layouts(rng, 64, 11)
+    env = BatchedMerlinEnv(N, enc=enc, agent=agent, device="cuda:0", n_actions=n_actions, max_steps=13, want_rgb=False)
+    assert env.obs is None and "sym" in env.step_kernel()
+    ref = fast.OracleVecEnv(N, enc, agent, n_actions=n_actions, max_steps=13, want_rgb=False)
+    rgb, sym = env.reset()
+    assert rgb is None and np.array_equal(_to_np(sym), ref.reset()[1])
+    for t in range(40):
+        a = rng.integers(0, n_actions, N)
+        obs, r, te, tr, info = env.step(torch.as_tensor(a, device="cuda:0"))
+        _, rr, rte, rtr, rinfo = ref.step(a)
+        assert obs is None
+        assert np.array_equal(_to_np(info["obs_symbolic"]), rinfo["obs_symbolic"]), t
+        assert np.array_equal(_to_np(r), rr) and np.array_equal(_to_np(te), rte) and np.array_equal(_to_np(tr), rtr), t
+        assert np.array_equal(_to_np(info["episode_length"]), rinfo["episode_length"]), t
+    assert np.array_equal(env.pose_numpy(), helpers.get_pose(ref))

@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--eval-tasks", type=int, default=100)
     ap.add_argument("--device-layouts", action="store_true",
                     help="generate the layout pool on the GPU (fresh layouts, not the reference's per-seed ones)")
+    ap.add_argument("--tf32-matmul", action="store_true",
+                    help="allow TF32 in the linear layers too (PyTorch's default keeps them in fp32; cuDNN convolutions "
+                         "already run TF32 by default)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="symbolic",
                     help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
@@ -68,6 +71,8 @@ def main():
 
     set_seed(a.seed + rank)
     torch.backends.cudnn.benchmark = True
+    if a.tf32_matmul:
+        torch.backends.cuda.matmul.allow_tf32 = True
     sc = ScenarioCreator()
     t_lay = time.perf_counter()
     per_rank = a.layouts // world
@@ -135,7 +140,7 @@ def main():
                           "cuda_graph_rollout": not a.no_graph, "obs_storage": a.obs_storage,
                           "rollout_obs_bytes": int(agent.buffer.states.numel() * agent.buffer.states.element_size()),
                           "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "layout_pool_per_gpu": per_rank,
-                          "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch), u8 frames", "seed": a.seed},
+                          "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch defaults: TF32 convolutions" + (", TF32 linear layers" if a.tf32_matmul else ", fp32 linear layers") + "), u8 frames", "seed": a.seed},
                "eval": {"tasks": a.eval_tasks, "seeds": "200000..", "mean_return": float(np.mean(r)),
                         "mean_steps": float(np.mean(n)), "success_rate": float(np.mean(g)), "eval_s": te},
                "train_log": log[:: max(1, len(log) // 20)] + log[-1:]}
