@@ -79,6 +79,8 @@ typedef struct merlin_step_extras {
   float* episode_return;   /* [N] sum of rewards of the episode that ended this step, else 0 */
   int32_t* episode_length; /* [N] its length, else 0 */
   uint8_t* stuck;          /* [N] info["stuck"] of StuckPenaltyWrapper */
+  float* done;             /* [N] 1.0f where terminated or truncated, else 0.0f: the `done` the reference's learners store
+                              (src/ppo.py:77,85; src/fomaml.py:72,81), written straight into a rollout row */
 } merlin_step_extras_t;
 
 void merlin_env_default_config(merlin_env_config_t* cfg);

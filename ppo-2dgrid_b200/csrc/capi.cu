@@ -338,7 +338,7 @@ int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, u
   EnvParams p = base_params(h);
   p.actions = actions; p.obs_rgb = obs_rgb; p.obs_sym = obs_sym;
   p.reward = reward; p.terminated = terminated; p.truncated = truncated;
-  if (extras) { p.out_ep_return = extras->episode_return; p.out_ep_length = extras->episode_length; p.out_stuck = extras->stuck; }
+  if (extras) { p.out_ep_return = extras->episode_return; p.out_ep_length = extras->episode_length; p.out_stuck = extras->stuck; p.out_done = extras->done; }
   cudaError_t err = launch_env_step(p, h->sm_count, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "env step launch");
   h->launches += 1;

@@ -148,6 +148,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
       if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
       if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
+        if (p.out_done) p.out_done[e] = done ? 1.f : 0.f;
       restart = done && f.auto_reset;
     }
   } else {
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
         if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
         if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
         if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
+        if (p.out_done) p.out_done[e] = done ? 1.f : 0.f;
       }
       restart = done && f.auto_reset;
     } else {

@@ -50,6 +50,7 @@ struct EnvParams {
   float* out_ep_return;
   int32_t* out_ep_length;
   uint8_t* out_stuck;
+  float* out_done;
 };
 
 // kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile,

@@ -34,7 +34,8 @@ class EnvConfig(C.Structure):
 
 
 class StepExtras(C.Structure):
-    _fields_ = [("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stuck", C.c_void_p)]
+    _fields_ = [("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stuck", C.c_void_p),
+                ("done", C.c_void_p)]
 
 
 _lib = None

@@ -22,18 +22,30 @@ SYM_SHAPE = (VIEW, VIEW, 3)
 
 
 class StepBuffers:
-    """Caller-owned per-step outputs of `BatchedMerlinEnv.step` (all `[N]`, on the env's device)."""
+    """Caller-owned per-step outputs of `BatchedMerlinEnv.step` (all `[N]`, on the env's device).  Any of them may be
+    a row of a rollout tensor (`StepBuffers(N, dev, reward=rewards[t], done=dones[t], ...)`): the step kernel then
+    writes the rollout directly and no copy kernels are needed."""
 
-    def __init__(self, num_envs, device):
+    def __init__(self, num_envs, device, reward=None, terminated=None, truncated=None, episode_return=None,
+                 episode_length=None, stuck=None, done=None):
         N, dev = num_envs, device
-        self.reward = torch.empty(N, dtype=torch.float32, device=dev)
-        self.terminated = torch.empty(N, dtype=torch.bool, device=dev)
-        self.truncated = torch.empty(N, dtype=torch.bool, device=dev)
-        self.episode_return = torch.empty(N, dtype=torch.float32, device=dev)
-        self.episode_length = torch.empty(N, dtype=torch.int32, device=dev)
-        self.stuck = torch.empty(N, dtype=torch.bool, device=dev)
+
+        def own(t, dtype):
+            if t is None:
+                return torch.empty(N, dtype=dtype, device=dev)
+            if t.shape != (N,) or t.dtype != dtype or not t.is_contiguous() or t.device != torch.device(dev):
+                raise ValueError(f"step output must be a contiguous {dtype} tensor of shape ({N},) on {dev}")
+            return t
+
+        self.reward = own(reward, torch.float32)
+        self.terminated = own(terminated, torch.bool)
+        self.truncated = own(truncated, torch.bool)
+        self.episode_return = own(episode_return, torch.float32)
+        self.episode_length = own(episode_length, torch.int32)
+        self.stuck = own(stuck, torch.bool)
+        self.done = own(done, torch.float32)
         self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
-                                       self.stuck.data_ptr())
+                                       self.stuck.data_ptr(), self.done.data_ptr())
 
 
 class BatchedMerlinEnv:
@@ -106,14 +118,16 @@ class BatchedMerlinEnv:
         self.episode_return = torch.empty(N, dtype=torch.float32, device=dev)
         self.episode_length = torch.empty(N, dtype=torch.int32, device=dev)
         self.stuck = torch.empty(N, dtype=torch.bool, device=dev)
+        self.done = torch.empty(N, dtype=torch.float32, device=dev)
         self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
-                                       self.stuck.data_ptr())
+                                       self.stuck.data_ptr(), self.done.data_ptr())
         self.n_envs = self.num_envs
 
-    def make_step_buffers(self):
-        """A private set of per-step outputs (reward, flags, episode stats) for `step(..., out=...)`: lets a caller keep
-        several steps in flight (e.g. copy step i's results to the host while step i+1 runs)."""
-        return StepBuffers(self.num_envs, self.device)
+    def make_step_buffers(self, **tensors):
+        """A private set of per-step outputs (reward, flags, done, episode stats) for `step(..., out=...)`: lets a caller
+        keep several steps in flight, or -- passing rows of its rollout tensors as keyword arguments -- have the step
+        kernel write the rollout directly."""
+        return StepBuffers(self.num_envs, self.device, **tensors)
 
     # ---- pool ------------------------------------------------------------------------------------
     def upload_layouts(self, cells, agent):
@@ -195,7 +209,7 @@ class BatchedMerlinEnv:
             sym.data_ptr() if sym is not None else None, b.reward.data_ptr(), b.terminated.data_ptr(),
             b.truncated.data_ptr(), C.byref(b._extras), self._stream()))
         info = {"episode_return": b.episode_return, "episode_length": b.episode_length, "stuck": b.stuck,
-                "obs_symbolic": sym}
+                "done": b.done, "obs_symbolic": sym}
         return obs, b.reward, b.terminated, b.truncated, info
 
     def render(self, obs_symbolic, index=None, out=None, blocked=False):

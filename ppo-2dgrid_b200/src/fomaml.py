@@ -104,21 +104,24 @@ class FOMAML:
     def _rollout_buffers(self, env, steps):
         B, dev = env.num_envs, env.device
         f32 = dict(dtype=torch.float32, device=dev)
-        return {"obs": torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev),
-                "act": torch.empty((steps, B), dtype=torch.long, device=dev), "rew": torch.empty((steps, B), **f32),
-                "val": torch.empty((steps, B), **f32), "logp": torch.empty((steps, B), **f32),
-                "done": torch.empty((steps, B), **f32), "ep_ret": torch.empty((steps, B), **f32),
-                "ep_len": torch.empty((steps, B), dtype=torch.int32, device=dev), "last_val": torch.empty(B, **f32)}
+        buf = {"obs": torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev),
+               "act": torch.empty((steps, B), dtype=torch.long, device=dev), "rew": torch.empty((steps, B), **f32),
+               "val": torch.empty((steps, B), **f32), "logp": torch.empty((steps, B), **f32),
+               "done": torch.empty((steps, B), **f32), "ep_ret": torch.empty((steps, B), **f32),
+               "ep_len": torch.empty((steps, B), dtype=torch.int32, device=dev), "last_val": torch.empty(B, **f32)}
+        # the step kernel writes reward / done / episode statistics of step t straight into row t
+        scratch = {k: torch.empty(B, dtype=torch.bool, device=dev) for k in ("terminated", "truncated", "stuck")}
+        buf["rows"] = [env.make_step_buffers(reward=buf["rew"][t], done=buf["done"][t], episode_return=buf["ep_ret"][t],
+                                             episode_length=buf["ep_len"][t], **scratch) for t in range(steps)]
+        return buf
 
     def _rollout_body(self, env, policy, params, steps, buf):
         obs = buf["obs"]
         env.reset(out_obs=obs[0])
         for t in range(steps):
             a, lp, v = self._act(policy, params, obs[t])
-            _, r, te, tr, info = env.step(a, out_obs=obs[t + 1])
-            buf["act"][t].copy_(a); buf["logp"][t].copy_(lp); buf["val"][t].copy_(v); buf["rew"][t].copy_(r)
-            buf["done"][t].copy_(te | tr)
-            buf["ep_ret"][t].copy_(info["episode_return"]); buf["ep_len"][t].copy_(info["episode_length"])
+            env.step(a, out_obs=obs[t + 1], out=buf["rows"][t])
+            buf["act"][t].copy_(a); buf["logp"][t].copy_(lp); buf["val"][t].copy_(v)
         buf["last_val"].copy_(self._act(policy, params, obs[steps])[2])
 
     @staticmethod

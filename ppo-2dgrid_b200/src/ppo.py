@@ -78,7 +78,14 @@ class PPO:
             self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
             self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
             self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
-            self._done_tmp = torch.zeros(N, dtype=torch.bool, device=self.device)
+            # the step kernel writes reward / done / episode statistics of step t straight into row t of these tensors
+            scratch = {k: torch.zeros(N, dtype=torch.bool, device=self.device) for k in ("terminated", "truncated", "stuck")}
+
+            def row(x, t):
+                return x[t] if x.dim() == 2 else x[t:t + 1]
+            self._rows = [env.make_step_buffers(reward=row(self.buffer.rewards, t), done=row(self.buffer.dones, t),
+                                                episode_return=self._ep_ret[t], episode_length=self._ep_len[t], **scratch)
+                          for t in range(T)]
         self.use_cuda_graph = bool(use_cuda_graph) and self.batched
         self._graph = None
 
@@ -107,17 +114,12 @@ class PPO:
             action, logp, value = self.ac.act(self._last_obs if sym else buf.obs_slot(t), deterministic=False)
             nxt = buf.obs_slot(t + 1) if t + 1 < T else (self._last_sym if sym else self._last_obs)
             if sym:
-                _, rew, term, trunc, info = env.step(action, out_obs=self._last_obs, out_symbolic=nxt)
+                env.step(action, out_obs=self._last_obs, out_symbolic=nxt, out=self._rows[t])
             else:
-                _, rew, term, trunc, info = env.step(action, out_obs=nxt)
+                env.step(action, out_obs=nxt, out=self._rows[t])
             buf.actions[t].copy_(action)
             buf.logprobs[t].copy_(logp)
             buf.values[t].copy_(value)
-            buf.rewards[t].copy_(rew)
-            torch.logical_or(term, trunc, out=self._done_tmp)
-            buf.dones[t].copy_(self._done_tmp)
-            self._ep_ret[t].copy_(info["episode_return"])
-            self._ep_len[t].copy_(info["episode_length"])
         self._last_value.copy_(self.ac.act(self._last_obs)[2])
 
     @torch.no_grad()

@@ -400,16 +400,14 @@ def test_outputs_stay_inside_their_buffers(N):
 
     rgb_all, rgb = guarded(N * 56 * 56 * 3)
     sym_all, sym = guarded(N * 147 + (-N * 147) % 16)
-    bufs = env.make_step_buffers()
-    raw = {}
-    for name, width in (("reward", 4), ("terminated", 1), ("truncated", 1), ("episode_return", 4), ("episode_length", 4),
-                        ("stuck", 1)):
+    raw, views = {}, {}
+    for name, dtype, width in (("reward", torch.float32, 4), ("terminated", torch.bool, 1), ("truncated", torch.bool, 1),
+                               ("episode_return", torch.float32, 4), ("episode_length", torch.int32, 4),
+                               ("stuck", torch.bool, 1), ("done", torch.float32, 4)):
         whole, inner = guarded(N * width + (-N * width) % 16)
         raw[name] = whole
-        t = getattr(bufs, name)
-        setattr(bufs, name, inner[: N * width].view(t.dtype))
-    from merlin_b200 import _lib
-    bufs._extras = _lib.StepExtras(bufs.episode_return.data_ptr(), bufs.episode_length.data_ptr(), bufs.stuck.data_ptr())
+        views[name] = inner[: N * width].view(dtype)
+    bufs = env.make_step_buffers(**views)  # the step kernel writes straight into these (rollout-row style)
     rgb_v, sym_v = rgb.view(N, 56, 56, 3), sym[: N * 147].view(N, 7, 7, 3)
     env.reset(out_obs=rgb_v, out_symbolic=sym_v)
     rng = np.random.default_rng(N)
@@ -419,4 +417,5 @@ def test_outputs_stay_inside_their_buffers(N):
     for whole in [rgb_all, sym_all] + list(raw.values()):
         assert bool((whole[:G] == 0xA5).all()) and bool((whole[-G:] == 0xA5).all())
     assert bool((sym_all[G + N * 147: G + sym.numel()] == 0xA5).all())  # padding after the last symbolic row
+    assert torch.equal(bufs.done, (bufs.terminated | bufs.truncated).float())
     assert 0 < int(bufs.episode_length.max()) <= 7 and not bool((rgb_v == 0xA5).all(dim=(1, 2, 3)).any())
