@@ -57,6 +57,25 @@ for diff in ("easy", "medium", "mediumhard", "hard", "hardest"):
             out["steps"] += 1
             if te or tr:
                 break
+# 3. random (difficulty, size, seed) triples, including continued streams (reset() without a seed, as PPO training does)
+cases = 0
+for k in range(60):
+    diff = ("easy", "medium", "mediumhard", "hard", "hardest")[int(rng.integers(0, 5))]
+    size = int(rng.integers(8, 27))
+    seed = int(rng.integers(0, 2**31 - 1))
+    sc2 = ScenarioCreator(shim.REFERENCE_ROOT + "/src/config/scenario.yaml")
+    sc2.config["difficulties"][diff]["params"]["size"] = size
+    env = sc2.create_env(diff)
+    env.reset(seed=seed)
+    stream = [env.unwrapped]
+    cells, agent = layouts.generate_stream(diff, size, seed, 3)
+    for j in range(3):
+        u = env.unwrapped
+        assert np.array_equal(codes.unpack_to_encoding(cells[j:j + 1], size, size)[0], u.grid.encode()), (diff, size, seed, j)
+        assert tuple(agent[j]) == (u.agent_pos[0], u.agent_pos[1], u.agent_dir), (diff, size, seed, j)
+        env.reset()
+    cases += 1
+out["random_layout_cases"] = cases
 print(json.dumps(out))
 '''.replace("REPO_ROOT_DIR", repr(ROOT))
 
@@ -66,4 +85,4 @@ def test_real_reference_modules_agree_with_product_logic():
     assert res.returncode == 0, res.stderr[-3000:]
     import json
     out = json.loads(res.stdout.strip().splitlines()[-1])
-    assert out["layouts"] == 15 and out["steps"] > 300
+    assert out["layouts"] == 15 and out["steps"] > 300 and out["random_layout_cases"] == 60

@@ -46,29 +46,3 @@ for blocked in (False, True):
             run()
         e1.record(); torch.cuda.synchronize()
         print(f"blocked={blocked} {phase}: {e0.elapsed_time(e1)/10:.3f} ms")
-
-# A/B: channels_last parameters
-agent.ac.blocked_first_layer = True
-agent.ac = agent.ac.to(memory_format=torch.channels_last)
-for phase in ("fwd4096", "fwdbwd16384"):
-    def run():
-        if phase == "fwd4096":
-            with torch.no_grad():
-                agent.ac.act(xs[:4096])
-        else:
-            lp, ent, v = agent.ac.evaluate(xs, acts)
-            (lp.mean() + v.mean() + ent.mean()).backward()
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        run()
-    e1.record(); torch.cuda.synchronize()
-    print(f"channels_last blocked=True {phase}: {e0.elapsed_time(e1)/10:.3f} ms")
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    lp, ent, v = agent.ac.evaluate(xs, acts)
-    (lp.mean() + v.mean() + ent.mean()).backward()
-    torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
