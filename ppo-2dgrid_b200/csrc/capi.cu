@@ -59,6 +59,7 @@ struct merlin_env {
   uint8_t* pool_cells = nullptr;
   uint32_t* pool_agent = nullptr;
   uint8_t* atlas = nullptr;
+  unsigned* sched = nullptr;             // [2] in-order tile scheduler of env_kernel_tile
   uint32_t* blit_lut = nullptr;
   uint8_t* atlas_blocked = nullptr;      // the atlas with every tile re-laid as four 4x4-pixel, channel-major blocks
   uint32_t* blit_lut_blocked = nullptr;
@@ -76,6 +77,7 @@ static EnvParams base_params(const merlin_env* h) {
   p.pool_cells = h->pool_cells; p.pool_agent = h->pool_agent; p.atlas = h->atlas; p.bad_actions = h->bad_actions;
   p.blit_lut = h->blit_lut;
   p.tile_present = h->tile_present;
+  p.sched = h->sched;
   return p;
 }
 
@@ -124,6 +126,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   ok = ok && cudaMalloc(&h->ep_return, N * sizeof(float)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->sched, 2 * sizeof(unsigned)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas_blocked, kAtlasBytes) == cudaSuccess;
@@ -139,6 +142,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   cudaMemset(h->ep_return, 0, N * sizeof(float));
   cudaMemset(h->bad_actions, 0, sizeof(unsigned long long));
   cudaMemset(h->atlas, 0, kAtlasBytes);
+  cudaMemset(h->sched, 0, 2 * sizeof(unsigned));
   {
     uint32_t lut[kChunksPerLane * 32];
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
@@ -160,7 +164,7 @@ int merlin_env_destroy(merlin_env_t* h) {
   DeviceGuard guard(h->cfg.device);
   cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
   cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
-  cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked); cudaFree(h->tile_present);
+  cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked); cudaFree(h->tile_present); cudaFree(h->sched);
   delete h;
   return MERLIN_OK;
 }

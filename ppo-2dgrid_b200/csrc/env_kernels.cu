@@ -301,14 +301,26 @@ __global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvPara
     load_lut(p, lane, lut);
   }
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // Tiles are handed out IN ORDER from a ticket counter rather than round-robin by CTA index: the CTAs' write fronts
+  // then stay inside one narrow, advancing window of the observation buffer, which is what keeps HBM writes near the
+  // plain-fill rate (measured with tools/cuda/write_pattern_bench.cu: 7.4 TB/s in order vs 6.4 TB/s with the static
+  // `tile += gridDim.x` assignment, whose CTAs drift apart).  Thread 32 draws the next ticket while warp 0 runs the
+  // state phase; the last CTA to finish rearms the counters for the next launch (also under CUDA-graph replay).
+  __shared__ int s_next;
+  if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+  __syncthreads();
+  int tile = s_next;
+  while (tile < n_tiles) {
     const int e0 = tile * T;
     if (warp == 0) {
       const unsigned m = state_phase<T, STEP>(p, f, e0, lane, kinds_s, sym_s);
       if (lane == 0) *mask_s = m;
+    } else if (threadIdx.x == 32) {
+      s_next = (int)atomicAdd(&p.sched[0], 1u);
     }
-    __syncthreads();  // kinds / sym / mask of this tile (and, first time round, the atlas) are in shared memory
+    __syncthreads();  // kinds / sym / mask of this tile, the next ticket (and, first time round, the atlas) are in smem
     const unsigned render_mask = *mask_s;
+    const int next = s_next;
     if (f.want_sym && render_mask)
       emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(T, p.N - e0), render_mask, threadIdx.x, blockDim.x);
     if (f.want_rgb) {
@@ -316,7 +328,12 @@ __global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvPara
         if ((render_mask >> i) & 1)
           blit_frame(atlas_s, kinds_s + i * kKindStride, lut, p.obs_rgb + (size_t)(e0 + i) * kImgBytes, lane);
     }
-    __syncthreads();  // the tile buffers are rewritten by the next state phase
+    __syncthreads();  // the tile buffers and the ticket slot are rewritten in the next round
+    tile = next;
+  }
+  if (threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+    p.sched[0] = 0;  // every CTA has drawn its last ticket: safe to rearm
+    p.sched[1] = 0;
   }
 }
 

@@ -35,6 +35,7 @@ struct EnvParams {
   uint32_t* visited;           // [N][vis_words] per-episode visited bitmap, or nullptr
   const uint8_t* pool_cells;   // [L][cell_stride]
   const uint32_t* pool_agent;  // [L] x | y<<8 | dir<<16
+  unsigned* sched;             // [2] tile ticket counter + finished-CTA counter of the tile kernel (self-resetting)
   const uint8_t* atlas;        // [128][192]
   const uint32_t* blit_lut;    // [kChunksPerLane][32] chunk -> (cell0, off0, cell1, off1), see chunk_lut()
   const uint32_t* tile_present;  // [4] device words; bit t set: atlas slot t can appear in a frame of this handle's pool

@@ -1,0 +1,149 @@
+// write_pattern_bench.cu -- how fast can 9408-byte frames be streamed to HBM under different work mappings?
+// (development aid for the frame phase of env_kernels.cu; no env logic, constant data, st.global.cs.v4 stores)
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/cuda/wpb tools/cuda/write_pattern_bench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+constexpr int kImg = 9408, kChunks = 588;
+
+__device__ __forceinline__ void st_cs(void* p, uint32_t a) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p), "r"(a) : "memory");
+}
+__device__ __forceinline__ void st_plain(void* p, uint32_t a) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p), "r"(a) : "memory");
+}
+
+// V0: flat -- thread i writes chunk i (what a vectorised fill does)
+template <bool CS> __global__ void k_flat(uint8_t* out, size_t n_chunks) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_chunks) { if (CS) st_cs(out + i * 16, (uint32_t)i); else st_plain(out + i * 16, (uint32_t)i); }
+}
+// V1: one warp per frame, persistent grid
+__global__ void k_warp_frame(uint8_t* out, int n_frames) {
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n_frames; f += warps) {
+    uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+  }
+}
+// V2: CTA tile of T frames, warps share them; optional busy-wait by warp 0 before each tile (models the state phase)
+__global__ void k_tile(uint8_t* out, int n_frames, int T, int delay_cycles) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int n_tiles = (n_frames + T - 1) / T;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (delay_cycles > 0) {
+      if (warp == 0) { const long long t0 = clock64(); while (clock64() - t0 < delay_cycles) {} }
+      __syncthreads();
+    }
+    for (int i = warp; i < T; i += wpc) {
+      const int f = tile * T + i;
+      if (f >= n_frames) break;
+      uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+      for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+    }
+    if (delay_cycles > 0) __syncthreads();
+  }
+}
+// V3: non-persistent: one CTA (8 warps) per 8 frames, in launch order
+__global__ void k_cta8(uint8_t* out, int n_frames) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = blockIdx.x * 8 + warp;
+  if (f >= n_frames) return;
+  uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+  for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+}
+
+// V4: tile per CTA, NON-persistent (grid = n_tiles, in launch order), optional warp-0 delay
+__global__ void k_tile_np(uint8_t* out, int n_frames, int T, int delay_cycles) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int tile = blockIdx.x;
+  if (delay_cycles > 0) {
+    if (warp == 0) { const long long t0 = clock64(); while (clock64() - t0 < delay_cycles) {} }
+    __syncthreads();
+  }
+  for (int i = warp; i < T; i += wpc) {
+    const int f = tile * T + i;
+    if (f >= n_frames) break;
+    uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+  }
+}
+// V5: persistent CTAs fetching tiles IN ORDER from an atomic counter (self-resetting), optional warp-0 delay
+__global__ void k_tile_dyn(uint8_t* out, int n_frames, int T, int delay_cycles, unsigned* sched) {
+  __shared__ int s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int n_tiles = (n_frames + T - 1) / T;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&sched[0], 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    if (delay_cycles > 0) {
+      if (warp == 0) { const long long t0 = clock64(); while (clock64() - t0 < delay_cycles) {} }
+      __syncthreads();
+    }
+    for (int i = warp; i < T; i += wpc) {
+      const int f = tile * T + i;
+      if (f >= n_frames) break;
+      uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+      for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+}
+
+template <typename F> float time_ms(F launch, int reps = 10) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int i = 0; i < 3; ++i) launch();
+  cudaEventRecord(a);
+  for (int i = 0; i < reps; ++i) launch();
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  return ms / reps;
+}
+
+int main(int argc, char** argv) {
+  const int N = argc > 1 ? atoi(argv[1]) : 1 << 20;
+  const size_t bytes = (size_t)N * kImg;
+  uint8_t* out; cudaMalloc(&out, bytes);
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  auto report = [&](const char* name, float ms) { printf("%-46s %8.1f us  %7.1f GB/s\n", name, ms * 1e3, bytes / ms / 1e6); };
+  const size_t n_chunks = (size_t)N * kChunks;
+  report("flat, plain st", time_ms([&] { k_flat<false><<<(unsigned)((n_chunks + 255) / 256), 256>>>(out, n_chunks); }));
+  report("flat, st.cs", time_ms([&] { k_flat<true><<<(unsigned)((n_chunks + 255) / 256), 256>>>(out, n_chunks); }));
+  for (int wps : {8, 16, 24, 32, 48, 64}) {
+    char name[96]; snprintf(name, sizeof name, "warp per frame, persistent, %d warps/SM", wps);
+    report(name, time_ms([&] { k_warp_frame<<<sms * wps / 8, 256>>>(out, N); }));
+  }
+  report("CTA(8 warps) per 8 frames, non-persistent", time_ms([&] { k_cta8<<<(N + 7) / 8, 256>>>(out, N); }));
+  for (int T : {8, 16, 32, 64}) for (int cps : {1, 2, 3, 4}) {
+    char name[96]; snprintf(name, sizeof name, "tile T=%d, %d CTAs/SM x 8 warps, no delay", T, cps);
+    report(name, time_ms([&] { k_tile<<<sms * cps, 256>>>(out, N, T, 0); }));
+  }
+  for (int delay : {2000, 5000, 10000}) for (int cps : {2, 3, 4}) {
+    char name[96]; snprintf(name, sizeof name, "tile T=32, %d CTAs/SM, warp0 busy %d cycles/tile", cps, delay);
+    report(name, time_ms([&] { k_tile<<<sms * cps, 256>>>(out, N, 32, delay); }));
+  }
+  unsigned* sched; cudaMalloc(&sched, 8); cudaMemset(sched, 0, 8);
+  for (int delay : {0, 2000, 5000, 10000}) {
+    char name[96];
+    for (int T : {16, 32}) {
+      snprintf(name, sizeof name, "tile T=%d NON-persistent, warp0 busy %d", T, delay);
+      report(name, time_ms([&] { k_tile_np<<<(N + T - 1) / T, 256>>>(out, N, T, delay); }));
+    }
+    for (int cps : {2, 3, 4}) {
+      snprintf(name, sizeof name, "tile T=32 dynamic in-order, %d CTAs/SM, busy %d", cps, delay);
+      report(name, time_ms([&] { k_tile_dyn<<<sms * cps, 256>>>(out, N, 32, delay, sched); }));
+    }
+  }
+  cudaFree(out);
+  return 0;
+}
