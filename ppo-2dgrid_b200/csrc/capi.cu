@@ -126,7 +126,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   ok = ok && cudaMalloc(&h->ep_return, N * sizeof(float)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->sched, 2 * sizeof(unsigned)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->sched, 4 * sizeof(unsigned)) == cudaSuccess;  // [0..1] step/reset, [2..3] render
   ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->atlas_blocked, kAtlasBytes) == cudaSuccess;
@@ -142,7 +142,7 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   cudaMemset(h->ep_return, 0, N * sizeof(float));
   cudaMemset(h->bad_actions, 0, sizeof(unsigned long long));
   cudaMemset(h->atlas, 0, kAtlasBytes);
-  cudaMemset(h->sched, 0, 2 * sizeof(unsigned));
+  cudaMemset(h->sched, 0, 4 * sizeof(unsigned));
   {
     uint32_t lut[kChunksPerLane * 32];
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
@@ -362,6 +362,7 @@ int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, c
   p.atlas = blocked ? h->atlas_blocked : h->atlas;
   p.lut = blocked ? h->blit_lut_blocked : h->blit_lut;
   p.tile_present = h->tile_present;
+  p.sched = h->sched + 2;
   cudaError_t err = launch_render(p, blocked != 0, h->sm_count, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "render launch");
   h->launches += 1;

@@ -270,21 +270,25 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 
 // ---------------------------------------------------------------------------------------------------
 // env_kernel_tile<T, STEP>: a CTA owns a tile of T <= 32 consecutive envs; warp 0 runs the state phase, every
-// warp of the CTA takes frames of the tile.  Two CTAs per SM overlap one tile's state phase with another's frames.
-// 256 threads, 2 CTAs per SM (128 registers): measured best on B200 (0.99 of the HBM copy peak at 1M envs).  Slower,
-// all between 0.69 and 0.94: 512-thread CTAs; 3 CTAs/SM at 80 registers; the blit map in shared memory; overlapping the
-// next tile's state phase with this tile's frames; all 8 warps writing ONE frame at a time (0.91); and splitting the
-// work into a state kernel + a high-occupancy frame-only kernel (0.84 at 24 warps/SM, 0.73 at 40: more concurrent
-// frame streams lower the achieved DRAM write bandwidth); 1 CTA/SM (0.71: nothing overlaps the state phase); 128-thread
-// CTAs x 2 (0.96) or x 4 (0.91); 64-env tiles with two state warps (0.94); 16-env tiles (0.84).  A plain vectorised fill reaches 7.4 TB/s on this part, so
-// ~14 % of DRAM headroom remains; the fused kernel's L1/LSU pipe is 76 % busy (ncu) and is the co-limit.
-constexpr int kTileThreads = 256;
+// warp of the CTA takes frames of the tile; co-resident CTAs overlap one tile's state phase with others' frames.
+// Shape (B200, 1M envs, RGB), all with tiles handed out in order (see the ticket scheduler below):
+//   T=16, 128 threads x 4 CTAs/SM   1.08 of the measured HBM copy peak (7.3e8 env-steps/s)   <- used
+//   T=32, 128 x 3: 1.08    T=32, 256 x 2: 1.06    T=32, 128 x 4: 1.06    T=16, 64 x 6: 1.07    T=8, 64 x 8: 1.04
+//   T=16, 128 x 5 (96 registers): 1.03    T=16, 128 x 6 (80 registers): 0.95    T=16, 256 x 2: 0.87
+// With the static `tile += gridDim.x` assignment the best shape (T=32, 256 x 2) reached 0.99 and every other one
+// 0.69-0.96.  Also slower: the blit map in shared memory (-7 %), overlapping the next tile's state phase inside the
+// CTA, all warps writing ONE frame at a time, plain / .cg / 256-bit stores instead of st.global.cs.v4, and a separate
+// state kernel + high-occupancy frame kernel with static assignment.  A plain vectorised fill reaches 7.4-7.6 TB/s on
+// this part and frames streamed in order without any env logic 7.4 TB/s (tools/cuda/write_pattern_bench.cu): the fused
+// kernel's 7.1 TB/s is 95 % of that.
+constexpr int kTileThreads = 128;
+constexpr int kTileCtasPerSm = 4;
 __host__ __device__ constexpr int tile_smem_bytes(int T) {
   return kAtlasBytes + ((T * kKindStride + T * kSymBytes + 15) & ~15) + 16;
 }
 
-template <int T, bool STEP>
-__global__ void __launch_bounds__(kTileThreads, 2) env_kernel_tile(const EnvParams p, const int n_tiles) {
+template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
+__global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams p, const int n_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -557,35 +561,52 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const RenderParams p) {
   for (int k = 0; k < kChunksPerLane; ++k) lut[k] = __ldg(p.lut + k * 32 + lane);
   __syncthreads();
 
-  for (int m = blockIdx.x * warps_per_cta + warp; m < p.M; m += gridDim.x * warps_per_cta) {
-    long long row = p.index ? p.index[m] : m;
-    if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;  // never read outside the buffer; callers validate indices
-    const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
+  // groups of kRenderGroup consecutive frames are drawn in order from a ticket counter (see env_kernel_tile)
+  constexpr int kRenderGroup = 32;
+  __shared__ int s_next;
+  const int n_groups = (p.M + kRenderGroup - 1) / kRenderGroup;
+  if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+  __syncthreads();
+  int group = s_next;
+  while (group < n_groups) {
+    __syncthreads();  // everyone has read the ticket
+    if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+    for (int m = group * kRenderGroup + warp; m < min(p.M, (group + 1) * kRenderGroup); m += warps_per_cta) {
+      long long row = p.index ? p.index[m] : m;
+      if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;  // never read outside the buffer; callers validate indices
+      const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = lane + 32 * h;  // cell index vi*7 + vj, the order Grid.encode stores them
-      if (k < kCells) {
-        const uint32_t t = sym[3 * k], c = sym[3 * k + 1], st = sym[3 * k + 2];
-        kp[k] = (uint8_t)kind_of_sym(t, c, st, k == (kView / 2) * kView + (kView - 1));
-      }
-    }
-    __syncwarp();
-    uint8_t* frame = p.out + (size_t)m * kImgBytes;
-    if (BLOCKED) {
-      const uint4* atlas128 = reinterpret_cast<const uint4*>(atlas_s);
-#pragma unroll
-      for (int k = 0; k < kChunksPerLane; ++k) {
-        const int c = lane + 32 * k;
-        if (c < kChunks) {
-          const uint32_t q = lut[k];
-          const uint4 v = atlas128[kp[q & 0xff] * (kTileBytes / 16) + (q >> 8)];
-          st_stream_v4(frame + c * 16, v.x, v.y, v.z, v.w);
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;  // cell index vi*7 + vj, the order Grid.encode stores them
+        if (k < kCells) {
+          const uint32_t t = sym[3 * k], c = sym[3 * k + 1], st = sym[3 * k + 2];
+          kp[k] = (uint8_t)kind_of_sym(t, c, st, k == (kView / 2) * kView + (kView - 1));
         }
       }
-    } else {
-      blit_frame(atlas_s, kp, lut, frame, lane);
+      __syncwarp();
+      uint8_t* frame = p.out + (size_t)m * kImgBytes;
+      if (BLOCKED) {
+        const uint4* atlas128 = reinterpret_cast<const uint4*>(atlas_s);
+#pragma unroll
+        for (int k = 0; k < kChunksPerLane; ++k) {
+          const int c = lane + 32 * k;
+          if (c < kChunks) {
+            const uint32_t q = lut[k];
+            const uint4 v = atlas128[kp[q & 0xff] * (kTileBytes / 16) + (q >> 8)];
+            st_stream_v4(frame + c * 16, v.x, v.y, v.z, v.w);
+          }
+        }
+      } else {
+        blit_frame(atlas_s, kp, lut, frame, lane);
+      }
+      __syncwarp();  // kp is reused by this warp's next frame
     }
-    __syncwarp();
+    __syncthreads();  // the next ticket is in shared memory
+    group = s_next;
+  }
+  if (threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
   }
 }
 
@@ -632,18 +653,19 @@ static cudaError_t launch_group_kernel(const EnvParams& p, int sm_count, cudaStr
   return cudaGetLastError();
 }
 
-template <int T, bool STEP>
+template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
 static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_smem_bytes(T);
   static int blocks_per_sm_dev[64] = {};
   int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
   if (!blocks_per_sm) {
-    cudaError_t err = resident_ctas(env_kernel_tile<T, STEP>, kTileThreads, smem, blocks_per_sm);
+    cudaError_t err = resident_ctas(env_kernel_tile<T, STEP, THREADS, MINB>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
+    if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
   const int grid = min(sm_count * blocks_per_sm, n_tiles);
-  env_kernel_tile<T, STEP><<<grid, kTileThreads, smem, stream>>>(p, n_tiles);
+  env_kernel_tile<T, STEP, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p, n_tiles);
   return cudaGetLastError();
 }
 
@@ -676,9 +698,8 @@ static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t s
   if (choice == 2) return launch_warp_kernel<STEP>(p, sm_count, stream);
   if (choice == 5) return launch_sym_kernel<STEP>(p, stream);
   if (choice == 3) {
-    // tiles of 32 envs once every SM gets a few; smaller tiles spread a small batch over more CTAs
-    if (p.N >= sm_count * 2 * 32) return launch_tile_kernel<32, STEP>(p, sm_count, stream);
-    if (p.N >= sm_count * 2 * 16) return launch_tile_kernel<16, STEP>(p, sm_count, stream);
+    // tiles of 16 envs once every resident CTA gets one; smaller tiles spread a small batch over more CTAs
+    if (p.N >= sm_count * kTileCtasPerSm * 16) return launch_tile_kernel<16, STEP>(p, sm_count, stream);
     return launch_tile_kernel<8, STEP>(p, sm_count, stream);
   }
   // pick the largest group size that still yields >= ~8 warps per SM; tiny batches use smaller groups
@@ -695,8 +716,7 @@ const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
   if (choice == 5) return "merlin::env_kernel_sym<true>";
   if (choice == 2) return "merlin::env_kernel_warp<true>";
   if (choice == 3)
-    return n_envs >= sm_count * 64 ? "merlin::env_kernel_tile<32,true>"
-                                   : (n_envs >= sm_count * 32 ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>");
+    return n_envs >= sm_count * kTileCtasPerSm * 16 ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>";
   const long long want_warps = (long long)sm_count * 8;
   if (n_envs / 32 >= want_warps) return "merlin::env_kernel<32,true>";
   if (n_envs / 16 >= want_warps) return "merlin::env_kernel<16,true>";

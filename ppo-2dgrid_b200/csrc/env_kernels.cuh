@@ -71,6 +71,7 @@ struct RenderParams {
   const uint8_t* atlas;      // [128][192]
   const uint32_t* lut;       // [kChunksPerLane][32]
   const uint32_t* tile_present;  // [4] device words
+  unsigned* sched;           // [2] in-order ticket counter + finished-CTA counter (self-resetting)
   int M;
   long long n_rows;          // rows of `sym` (index bound), 0 = unchecked
 };
