@@ -26,6 +26,11 @@ def main():
     ap.add_argument("--sizes", default="16,24,32,48,64")
     ap.add_argument("--tasks", type=int, default=100)
     ap.add_argument("--first-seed", type=int, default=200000)
+    ap.add_argument("--adapt-steps", type=int, default=0,
+                    help="> 0: few-shot evaluation -- every task first takes this many inner SGD steps from the checkpoint "
+                         "(FOMAML.few_shot_evaluate, src/distribution_over_tasks.py:132-209) before its greedy episode")
+    ap.add_argument("--k-support", type=int, default=256)
+    ap.add_argument("--lr-inner", type=float, default=0.01)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
 
@@ -54,7 +59,18 @@ def main():
     for size in [int(s) for s in a.sizes.split(",")]:
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        r, n, g = evaluate_seeds(policy, a.difficulty, size, mine, device=dev) if mine else (np.zeros(0),) * 3
+        if not mine:
+            r, n, g = (np.zeros(0),) * 3
+        elif a.adapt_steps > 0:
+            from src.fomaml import FOMAML
+            from src.scenario_creator.scenario_creator import ScenarioCreator
+            sc = ScenarioCreator()
+            sc.config["difficulties"][a.difficulty]["params"]["size"] = size
+            fo = FOMAML(sc, lr_inner=a.lr_inner, device=dev, difficulty=a.difficulty)
+            fo.meta_policy.load_state_dict(policy.state_dict())
+            r, n, g = fo.few_shot_evaluate(mine, k_support=a.k_support, adapt_steps=a.adapt_steps)
+        else:
+            r, n, g = evaluate_seeds(policy, a.difficulty, size, mine, device=dev)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if world > 1:
@@ -72,7 +88,9 @@ def main():
     if rank == 0 and a.out:
         with open(a.out, "w") as f:
             json.dump({"what": f"config 5: {a.difficulty} scale-generalisation sweep, greedy policy, seeds {a.first_seed}..",
-                       "n_gpus": world, "checkpoint": a.ckpt or "random init", "rows": rows}, f, indent=1)
+                       "n_gpus": world, "checkpoint": a.ckpt or "random init",
+                       "mode": f"few-shot: {a.adapt_steps} inner step(s) on {a.k_support} support transitions, lr {a.lr_inner}"
+                               if a.adapt_steps else "zero-shot", "rows": rows}, f, indent=1)
     if world > 1:
         dist.destroy_process_group()
 

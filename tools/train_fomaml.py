@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--seed", type=int, default=777)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--save", default=None, help="path for the final meta-policy state_dict (.pth, reference format)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
 
@@ -93,6 +94,8 @@ def main():
                                              f"k query + backward) = {cb['seconds_per_task']:.2f} s, reference-style "
                                              "serial loop, literal minigrid restatement, torch CPU; x tasks_per_batch",
                                    "s_per_iteration": per_iter, "projected_wall_s_1000_iterations": 1000 * per_iter}
+        if a.save:
+            torch.save(fo.meta_policy.state_dict(), a.save)
         print(json.dumps(out), flush=True)
         if a.out:
             with open(a.out, "w") as f:
