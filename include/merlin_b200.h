@@ -132,6 +132,11 @@ int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, u
 int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
                       uint8_t* out, int32_t blocked, void* stream);
 
+/* The fully observable symbolic observation of every env's CURRENT state -- minigrid FullyObsWrapper.observation,
+ * which the reference selects with `observation.fully_observable: true` (src/scenario_creator/scenario_creator.py:45-46):
+ * out: DEVICE u8[N][W][H][3], Grid.encode() indexed [x][y][type, colour, state], the agent's cell = (10, 0, agent_dir). */
+int merlin_env_full_obs(merlin_env_t* h, uint8_t* out, void* stream);
+
 /* State views: DEVICE pointers owned by the handle (valid until destroy). */
 int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state_xyds /* int4[N]: pose,step_count,cursor,stuck */,
                           uint8_t** cells /* [N][cell_stride] or NULL when grids are immutable */,

@@ -369,6 +369,17 @@ int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, c
   return MERLIN_OK;
 }
 
+int merlin_env_full_obs(merlin_env_t* h, uint8_t* out, void* stream) {
+  if (!h || !out) return fail(MERLIN_EINVAL, "merlin_env_full_obs: null argument");
+  if (!h->was_reset) return fail(MERLIN_ESTATE, "full observation requested before reset");
+  DeviceGuard guard(h->cfg.device);
+  EnvParams p = base_params(h);
+  cudaError_t err = launch_full_obs(p, out, h->sm_count, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "full observation launch");
+  h->launches += 1;
+  return MERLIN_OK;
+}
+
 int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state, uint8_t** cells, int32_t* cell_stride, float** episode_return) {
   if (!h) return fail(MERLIN_EINVAL, "null handle");
   if (state) *state = reinterpret_cast<int32_t*>(h->state);

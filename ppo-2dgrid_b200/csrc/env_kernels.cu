@@ -621,6 +621,36 @@ cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cud
 }
 
 // ---------------------------------------------------------------------------------------------------
+// full_obs_kernel: the fully observable symbolic observation (minigrid FullyObsWrapper; selected by
+// `observation.fully_observable: true` in the reference's scenario.yaml, src/scenario_creator/scenario_creator.py:45-46).
+// One thread per output cell, output-order indexing (coalesced 3-byte cells; the 256-byte grids are read through L1).
+__global__ void __launch_bounds__(256) full_obs_kernel(const EnvParams p, uint8_t* __restrict__ out) {
+  const long long cells_per_env = (long long)p.W * p.H;
+  const long long total = cells_per_env * p.N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / cells_per_env);
+    const int c = (int)(i - (long long)e * cells_per_env);
+    const int x = c / p.H, y = c - x * p.H;  // output index [x][y]
+    const int4 st = p.state[e];
+    EnvState s{};
+    unpack_state(st.x, st.y, st.z, st.w, s);
+    const uint8_t* grid = p.cells ? p.cells + (size_t)e * p.cell_stride
+                                  : p.pool_cells + (size_t)(s.layout < 0 ? ~s.layout : s.layout) * p.cell_stride;
+    uint8_t t, col, stt;
+    if (x == s.x && y == s.y) { t = (uint8_t)T_AGENT; col = 0; stt = (uint8_t)s.dir; }
+    else sym_of_code(grid[y * p.W + x], t, col, stt);
+    out[i * 3 + 0] = t; out[i * 3 + 1] = col; out[i * 3 + 2] = stt;
+  }
+}
+
+cudaError_t launch_full_obs(const EnvParams& p, uint8_t* out, int sm_count, cudaStream_t stream) {
+  const long long total = (long long)p.W * p.H * p.N;
+  const int grid = (int)min((long long)sm_count * 8, (total + 255) / 256);
+  full_obs_kernel<<<grid, 256, 0, stream>>>(p, out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // launch helpers: persistent grids of (SMs x resident CTAs), capped by the work available
 template <typename Kernel>
 static cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int& blocks_per_sm) {

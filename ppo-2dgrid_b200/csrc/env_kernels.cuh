@@ -81,6 +81,9 @@ cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cud
 cudaError_t launch_layouts(uint8_t* pool_cells, uint32_t* pool_agent, int cell_stride, int W, int H, int difficulty,
                            uint64_t seed, long long first_number, int first_slot, int count, int sm_count,
                            cudaStream_t stream);
+// FullyObsWrapper.observation for every env: Grid.encode() of the current grid, u8[N][W][H][3] indexed [x][y][c],
+// with the agent's cell replaced by (OBJECT_TO_IDX["agent"] = 10, COLOR_TO_IDX["red"] = 0, agent_dir).
+cudaError_t launch_full_obs(const EnvParams& p, uint8_t* out, int sm_count, cudaStream_t stream);
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream);
 

@@ -212,6 +212,17 @@ class BatchedMerlinEnv:
                 "done": b.done, "obs_symbolic": sym}
         return obs, b.reward, b.terminated, b.truncated, info
 
+    def full_observation(self, out=None):
+        """FullyObsWrapper's observation of every env's current state: u8[N, W, H, 3] (`Grid.encode()` indexed [x][y],
+        the agent's cell = (10, 0, agent_dir))."""
+        shape = (self.num_envs, self.width, self.height, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous uint8 tensor of shape {shape}")
+        _lib.check(self._lib.merlin_env_full_obs(self._h, out.data_ptr(), self._stream()))
+        return out
+
     def render(self, obs_symbolic, index=None, out=None, blocked=False):
         """Frames from stored symbolic observations: `obs_symbolic` u8[R, 7, 7, 3] (any leading shape, contiguous),
         `index` optional int64[M] rows to render (a minibatch gather fused with the rendering).

@@ -178,6 +178,10 @@ class BaseCustomEnv:
         """The underlying N = 1 BatchedMerlinEnv (device tensors)."""
         return self._venv
 
+    def gen_full_obs(self):
+        """FullyObsWrapper's image for the current state: u8[W, H, 3], computed on the device."""
+        return self._venv.full_observation()[0].cpu().numpy()
+
     def get_pov_render(self, tile_size=None):
         """The 56x56x3 egocentric frame of the current state (RGBImgPartialObsWrapper's observation)."""
         return self._obs_rgb

@@ -13,7 +13,7 @@ import numpy as np
 import yaml
 
 import src.custom_envs.register as _register  # noqa: F401  (registration side effect, as in the reference)
-from src.wrappers.obs_wrappers import FlattenObservation, ImgObsWrapper, RGBImgPartialObsWrapper
+from src.wrappers.obs_wrappers import FlattenObservation, FullyObsWrapper, ImgObsWrapper, RGBImgPartialObsWrapper
 from src.wrappers.three_action_wrapper import ThreeActionWrapper
 
 DEFAULT_CONFIG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "scenario.yaml")
@@ -56,9 +56,10 @@ class ScenarioCreator:
         cfg = self._difficulty_cfg(difficulty)
         env = _register.make(cfg["env_id"], **{**self.global_cfg, **cfg.get("params", {})})
         if self.obs_cfg.get("fully_observable", False):
-            raise NotImplementedError("fully_observable observations are not produced by the CUDA path "
-                                      "(the reference's scenario.yaml ships fully_observable: false)")
-        env = ImgObsWrapper(RGBImgPartialObsWrapper(env))
+            env = FullyObsWrapper(env)
+        else:
+            env = RGBImgPartialObsWrapper(env)
+        env = ImgObsWrapper(env)
         if self.obs_cfg.get("flatten", False):
             env = FlattenObservation(env)
         return ThreeActionWrapper(env)

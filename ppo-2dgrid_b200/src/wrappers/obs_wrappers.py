@@ -31,6 +31,28 @@ class RGBImgPartialObsWrapper(Wrapper):
         return self.observation(obs), r, te, tr, info
 
 
+class FullyObsWrapper(Wrapper):
+    """minigrid FullyObsWrapper (`observation.fully_observable: true`): the whole grid as `Grid.encode()` with the
+    agent's cell marked (10, 0, dir); produced by merlin_env_full_obs."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        u = env.unwrapped
+        self.observation_space = dict(env.observation_space)
+        self.observation_space["image"] = Box(0, 255, (u.width, u.height, 3), np.uint8)
+
+    def observation(self, obs):
+        return {**obs, "image": self.unwrapped.gen_full_obs()}
+
+    def reset(self, **kwargs):
+        obs, info = self.env.reset(**kwargs)
+        return self.observation(obs), info
+
+    def step(self, action):
+        obs, r, te, tr, info = self.env.step(action)
+        return self.observation(obs), r, te, tr, info
+
+
 class ImgObsWrapper(Wrapper):
     def __init__(self, env):
         super().__init__(env)

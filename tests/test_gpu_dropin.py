@@ -368,3 +368,58 @@ def test_symbolic_only_observations(N, n_actions):
         assert np.array_equal(_to_np(r), rr) and np.array_equal(_to_np(te), rte) and np.array_equal(_to_np(tr), rtr), t
         assert np.array_equal(_to_np(info["episode_length"]), rinfo["episode_length"]), t
     assert np.array_equal(env.pose_numpy(), helpers.get_pose(ref))
+
+
+# ---- fully observable observations (scenario.yaml: observation.fully_observable / flatten) ----------------------------
+def test_fully_observable_and_flatten_match_the_reference_wrappers():
+    from oracle import merlin_ref as mr
+    from merlin_b200 import BatchedMerlinEnv, codes, layouts
+    sc = _sc()
+    sc.obs_cfg = {"fully_observable": True, "flatten": True}
+    env = sc.create_env("hardest")
+    ref = mr.make_env("hardest", size=16, fully_observable=True, flatten=True)
+    obs, _ = env.reset(seed=21)
+    robs, _ = ref.reset(seed=21)
+    assert obs.shape == (16 * 16 * 3,) and obs.dtype == np.uint8 and env.observation_space.shape == (768,)
+    assert np.array_equal(obs, robs)
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        a = int(rng.integers(0, 3))
+        obs, r, te, tr, _ = env.step(a)
+        robs, rr, rte, rtr, _ = ref.step(a)
+        assert np.array_equal(obs, robs) and np.float32(r) == np.float32(rr) and (te, tr) == (rte, rtr), t
+        if te or tr:
+            obs, _ = env.reset()
+            assert np.array_equal(obs, ref.reset()[0])
+    env.close()
+    # batched, 7 actions with doors / keys / carried objects: every env's full grid incl. the agent marker
+    from test_gpu_parity import _object_layouts
+    enc, agent = _object_layouts(np.random.default_rng(5), 32, 11)
+    N = 500
+    venv = BatchedMerlinEnv(N, enc=enc, agent=agent, device="cuda:0", n_actions=7, max_steps=30)
+    oref = fast.OracleVecEnv(N, enc, agent, n_actions=7, max_steps=30)
+    venv.reset()
+    oref.reset()
+    for t in range(25):
+        a = rng.integers(0, 7, N)
+        venv.step(torch.as_tensor(a, device="cuda:0"))
+        oref.step(a)
+    full = venv.full_observation().cpu().numpy()
+    want = np.stack([oref.gt, oref.gc, oref.gs], axis=-1).reshape(N, 11, 11, 3).transpose(0, 2, 1, 3).copy()
+    want[np.arange(N), oref.ax, oref.ay] = np.stack([np.full(N, 10), np.zeros(N, int), oref.adir], axis=-1)
+    assert full.shape == (N, 11, 11, 3) and np.array_equal(full, want)
+
+
+def test_ppo_mlp_on_flattened_fully_observable_env():
+    """The reference's MLP branch (src/ppo.py:38-41): 1-D observations -> MLPActorCritic."""
+    from src.ppo import PPO
+    torch.manual_seed(0)
+    sc = _sc()
+    sc.obs_cfg = {"fully_observable": True, "flatten": True}
+    env = sc.create_env("medium")
+    env.reset(seed=2)
+    agent = PPO(env, batch_size=48, minibatch_size=24, update_epochs=1, device="cuda:0")
+    assert not agent.use_cnn and agent.obs_shape == (768,)
+    m = agent.update(agent.collect_rollouts())
+    assert np.isfinite(m["pi_loss"]) and np.isfinite(m["entropy"])
+    env.close()
