@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 // With the static `tile += gridDim.x` assignment the best shape (T=32, 256 x 2) reached 0.99 and every other one
 // 0.69-0.96.  Also slower: the blit map in shared memory (-7 %), overlapping the next tile's state phase inside the
 // CTA, all warps writing ONE frame at a time, plain / .cg / 256-bit stores instead of st.global.cs.v4, and a separate
-// state kernel + high-occupancy frame kernel with static assignment.  A plain vectorised fill reaches 7.4-7.6 TB/s on
+// state kernel + high-occupancy frame kernel with static assignment.  Padding the shared-memory atlas slots to remove
+// the 17 % bank conflicts changes nothing (the store stream, not the LSU, is the limit).  A plain vectorised fill reaches 7.4-7.6 TB/s on
 // this part and frames streamed in order without any env logic 7.4 TB/s (tools/cuda/write_pattern_bench.cu): the fused
 // kernel's 7.1 TB/s is 95 % of that.
 constexpr int kTileThreads = 128;
