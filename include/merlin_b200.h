@@ -28,7 +28,9 @@
  *     and copy.  Env state lives in device memory owned by the handle.
  *   - reset/step/gae are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
  *     legacy default stream), allocate nothing, never synchronise, and may be captured in a CUDA graph.
- *   - A handle is not thread-safe; one caller thread per handle.  One handle per device.
+ *   - A handle is not thread-safe; one caller thread per handle.  One handle per device.  Calls on one handle must be
+ *     stream-ordered with respect to each other (reset/step share an in-kernel tile scheduler, so do concurrent
+ *     merlin_env_render calls): use one stream per handle, or order streams with events.
  *   - There is no CPU fallback: without a CUDA device every entry point fails with MERLIN_ECUDA.
  *
  * Packed cell code (1 byte per grid cell, row-major [y*W + x]):
