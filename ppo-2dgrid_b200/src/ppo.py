@@ -117,9 +117,10 @@ class PPO:
                 env.step(action, out_obs=self._last_obs, out_symbolic=nxt, out=self._rows[t])
             else:
                 env.step(action, out_obs=nxt, out=self._rows[t])
-            buf.actions[t].copy_(action)
-            buf.logprobs[t].copy_(logp)
-            buf.values[t].copy_(value)
+            shape = buf.actions[t].shape  # [N], or [] for a single batched env (the reference's [T] buffers)
+            buf.actions[t].copy_(action.reshape(shape))
+            buf.logprobs[t].copy_(logp.reshape(shape))
+            buf.values[t].copy_(value.reshape(shape))
         self._last_value.copy_(self.ac.act(self._last_obs)[2])
 
     @torch.no_grad()

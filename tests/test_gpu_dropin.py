@@ -213,6 +213,19 @@ def test_ppo_symbolic_rollout_storage_equals_frame_storage():
         assert torch.allclose(pa, pb, atol=1e-5)
 
 
+def test_batched_ppo_with_a_single_env_uses_reference_shaped_buffers():
+    """N = 1 batched env = the reference regime (1 env x T steps) with device-resident rollouts: [T] buffers."""
+    from src.ppo import PPO
+    torch.manual_seed(0)
+    env = _sc().create_batched_env("mediumhard", 1, device="cuda:0", seeds=range(300, 364), max_steps=30)
+    agent = PPO(env, batch_size=96, minibatch_size=32, update_epochs=2)
+    lv = agent.collect_rollouts()
+    assert agent.buffer.rewards.shape == (96,) and agent.buffer.states.shape == (96, 56, 56, 3) and lv.shape == (1,)
+    assert int(agent.buffer.dones.sum()) >= 3 and len(agent.episode_lengths) == int(agent.buffer.dones.sum())
+    m = agent.update(lv)
+    assert np.isfinite(m["pi_loss"]) and np.isfinite(m["kl"])
+
+
 def test_single_env_ppo_reference_loop_runs_on_the_cuda_env():
     from src.ppo import PPO
     torch.manual_seed(0)
