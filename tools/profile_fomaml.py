@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""Wall-clock split of one FOMAML meta-iteration (config 4 shapes): env setup, support / query rollouts, losses, grads."""
 import os, sys, time
-sys.path[:0] = ["/root/repo", "/root/repo/ppo-2dgrid_b200"]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "ppo-2dgrid_b200")]
 import numpy as np, torch
 from src.fomaml import FOMAML, _stack
 from src.scenario_creator.scenario_creator import ScenarioCreator
