@@ -28,13 +28,15 @@ from .rollout_buffer import RolloutBuffer
 class PPO:
     def __init__(self, env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
                  minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False,
-                 obs_storage="rgb"):
+                 obs_storage="rgb", amp_dtype=None):
         self.env = env
         self.batched = isinstance(env, BatchedMerlinEnv)
         self.device = env.device if self.batched else torch.device(device)
         self.gamma, self.lam, self.clip_eps = gamma, lam, clip_eps
         self.update_epochs, self.batch_size, self.minibatch_size = update_epochs, batch_size, minibatch_size
         self.vf_coef, self.ent_coef = vf_coef, ent_coef
+        # optional reduced-precision policy evaluation in the update (torch.autocast); None = fp32 like the reference
+        self.amp_dtype = amp_dtype
 
         if obs_storage not in ("rgb", "symbolic"):
             raise ValueError("obs_storage must be 'rgb' (56x56x3 frames in the rollout) or 'symbolic' (7x7x3, expanded on read)")
@@ -200,7 +202,9 @@ class PPO:
             idxs = torch.randperm(n, device=self.device)
             for start in range(0, n, self.minibatch_size):
                 mb = idxs[start: start + self.minibatch_size]
-                logp_new, entropy, values = self.ac.evaluate(frames(mb), actions[mb])
+                with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+                    logp_new, entropy, values = self.ac.evaluate(frames(mb), actions[mb])
+                logp_new, entropy, values = logp_new.float(), entropy.float(), values.float()
                 mb_adv, mb_old = adv[mb], logprobs_old[mb]
                 ratio = torch.exp(logp_new - mb_old)
                 surr = torch.min(ratio * mb_adv, torch.clamp(ratio, 1 - self.clip_eps, 1 + self.clip_eps) * mb_adv)

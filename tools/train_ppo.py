@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--tf32-matmul", action="store_true",
                     help="allow TF32 in the linear layers too (PyTorch's default keeps them in fp32; cuDNN convolutions "
                          "already run TF32 by default)")
+    ap.add_argument("--amp", choices=["none", "bf16"], default="none",
+                    help="bf16 autocast for the policy evaluation in the update (reduced precision: not the headline setting)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="symbolic",
                     help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
@@ -93,7 +95,8 @@ def main():
     t_lay = time.perf_counter() - t_lay
     agent = PPO(env, lr=a.lr, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=a.update_epochs,
                 batch_size=a.envs * a.horizon, minibatch_size=a.minibatch, vf_coef=0.5, ent_coef=a.ent_coef,
-                use_cuda_graph=not a.no_graph, obs_storage=a.obs_storage)
+                use_cuda_graph=not a.no_graph, obs_storage=a.obs_storage,
+                amp_dtype=torch.bfloat16 if a.amp == "bf16" else None)
 
     def sync():
         if world > 1:
@@ -140,7 +143,7 @@ def main():
                           "cuda_graph_rollout": not a.no_graph, "obs_storage": a.obs_storage,
                           "rollout_obs_bytes": int(agent.buffer.states.numel() * agent.buffer.states.element_size()),
                           "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "layout_pool_per_gpu": per_rank,
-                          "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch defaults: TF32 convolutions" + (", TF32 linear layers" if a.tf32_matmul else ", fp32 linear layers") + "), u8 frames", "seed": a.seed},
+                          "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch defaults: TF32 convolutions" + (", TF32 linear layers" if a.tf32_matmul else ", fp32 linear layers") + ")" + (", bf16 autocast in the update" if a.amp == "bf16" else "") + ", u8 frames", "seed": a.seed},
                "eval": {"tasks": a.eval_tasks, "seeds": "200000..", "mean_return": float(np.mean(r)),
                         "mean_steps": float(np.mean(n)), "success_rate": float(np.mean(g)), "eval_s": te},
                "train_log": log[:: max(1, len(log) // 20)] + log[-1:]}
