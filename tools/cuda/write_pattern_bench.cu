@@ -100,6 +100,56 @@ __global__ void k_tile_dyn(uint8_t* out, int n_frames, int T, int delay_cycles, 
   if (threadIdx.x == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }
 
+// V6: in-order tiles + the per-env side traffic of the real step kernel: warp 0 reads state (16 B), action (8 B) and
+// episode return (4 B) per env and writes state, return, reward and two flags back.  HINT: 0 plain, 1 = L2 evict_last
+// policy on those side accesses (keep the 30 MB of per-env state resident in L2 across launches).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <int HINT>
+__global__ void k_tile_side(uint8_t* out, int n_frames, int T, unsigned* sched, int4* state, const long long* actions,
+                            float* ep_ret, float* reward, uint8_t* term, uint8_t* trunc) {
+  __shared__ int s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int n_tiles = (n_frames + T - 1) / T;
+  const uint64_t pol = policy_evict_last();
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&sched[0], 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) break;
+    if (warp == 0 && lane < T) {
+      const int e = tile * T + lane;
+      if (e < n_frames) {
+        int4 st; long long a; float r;
+        if (HINT) {
+          asm volatile("ld.global.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(st.x), "=r"(st.y), "=r"(st.z), "=r"(st.w) : "l"(state + e), "l"(pol));
+          asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(a) : "l"(actions + e), "l"(pol));
+          asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ep_ret + e), "l"(pol));
+        } else { st = state[e]; a = actions[e]; r = ep_ret[e]; }
+        st.y += (int)a; r += 1.0f;
+        if (HINT) {
+          asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(state + e), "r"(st.x), "r"(st.y), "r"(st.z), "r"(st.w), "l"(pol) : "memory");
+          asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(ep_ret + e), "f"(r), "l"(pol) : "memory");
+        } else { state[e] = st; ep_ret[e] = r; }
+        reward[e] = r; term[e] = 0; trunc[e] = (uint8_t)(st.y & 1);
+      }
+    }
+    __syncthreads();
+    for (int i = warp; i < T; i += wpc) {
+      const int f = tile * T + i;
+      if (f >= n_frames) break;
+      uint8_t* frame = out + (size_t)f * kImg;
+#pragma unroll
+      for (int k = 0; k < 19; ++k) { const int c = lane + 32 * k; if (c < kChunks) st_cs(frame + c * 16, f); }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+}
+
 template <typename F> float time_ms(F launch, int reps = 10) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < 3; ++i) launch();
@@ -144,6 +194,13 @@ int main(int argc, char** argv) {
       report(name, time_ms([&] { k_tile_dyn<<<sms * cps, 256>>>(out, N, 32, delay, sched); }));
     }
   }
+  int4* state; long long* actions; float *ep_ret, *reward; uint8_t *term, *trunc;
+  cudaMalloc(&state, (size_t)N * 16); cudaMalloc(&actions, (size_t)N * 8); cudaMalloc(&ep_ret, (size_t)N * 4);
+  cudaMalloc(&reward, (size_t)N * 4); cudaMalloc(&term, N); cudaMalloc(&trunc, N);
+  cudaMemset(state, 0, (size_t)N * 16); cudaMemset(actions, 0, (size_t)N * 8); cudaMemset(ep_ret, 0, (size_t)N * 4);
+  report("tile T=16 in-order 128thr x4 + side traffic, plain", time_ms([&] { k_tile_side<0><<<sms * 4, 128>>>(out, N, 16, sched, state, actions, ep_ret, reward, term, trunc); }));
+  report("tile T=16 in-order 128thr x4 + side traffic, evict_last", time_ms([&] { k_tile_side<1><<<sms * 4, 128>>>(out, N, 16, sched, state, actions, ep_ret, reward, term, trunc); }));
+  report("tile T=16 in-order 128thr x4, no side traffic", time_ms([&] { k_tile_dyn<<<sms * 4, 128>>>(out, N, 16, 0, sched); }));
   cudaFree(out);
   return 0;
 }
