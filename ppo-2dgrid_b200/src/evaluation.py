@@ -82,3 +82,32 @@ def evaluate_model(sc, policy, difficulty, seeds, device="cuda"):
     size = int(sc.config["difficulties"][difficulty].get("params", {}).get("size", 16))
     r, n, _ = evaluate_seeds(policy, diff, size, seeds, device=device)
     return float(np.mean(r)), float(np.mean(n))
+
+
+def load_policy(model_path, env=None, device="cuda", obs_shape=(56, 56, 3), act_dim=3):
+    """A policy from a reference-format `.pth` state_dict (src/sweep_checkpoints.py:19-50): CNN for image observations,
+    MLP for flat ones; checkpoints of the older shared-trunk architecture (keys `feature_extractor.conv.*`) are mapped
+    onto both the actor and the critic trunk, the remaining keys loaded non-strictly, as the reference does.
+    `env` (optional) supplies observation shape and action count; returns (policy in eval mode, use_cnn)."""
+    from .actor_critic import CNNActorCritic, MLPActorCritic
+    if env is not None:
+        space = getattr(env, "observation_space", None)
+        if space is not None and hasattr(space, "shape"):
+            obs_shape = tuple(space.shape)
+        act_dim = getattr(getattr(env, "action_space", None), "n", act_dim)
+    use_cnn = len(obs_shape) == 3
+    policy = (CNNActorCritic(obs_shape, act_dim) if use_cnn else MLPActorCritic(int(np.prod(obs_shape)), act_dim)).to(device)
+    state = torch.load(model_path, map_location=device, weights_only=True)
+    if use_cnn and any("feature_extractor" in k for k in state):
+        mapped = {}
+        for k, v in state.items():
+            if "feature_extractor.conv" in k:
+                for trunk in ("actor_extractor.network", "critic_extractor.network"):
+                    mapped[k.replace("feature_extractor.conv", trunk)] = v.clone()
+            else:
+                mapped[k] = v
+        policy.load_state_dict(mapped, strict=False)
+    else:
+        policy.load_state_dict(state)
+    policy.eval()
+    return policy, use_cnn

@@ -212,3 +212,30 @@ def test_blocked_first_layer_is_the_same_function():
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
     l3, v3 = ac(obs.float())  # float NHWC copies (the reference's buffer dtype) take the same path
     assert torch.allclose(l3, l2, atol=1e-6)
+
+
+def test_load_policy_current_and_legacy_checkpoints(tmp_path):
+    """Reference-format checkpoints load; the older shared-trunk layout is mapped onto both trunks (sweep_checkpoints.py:19-50)."""
+    from src.evaluation import load_policy
+    torch.manual_seed(3)
+    ac = CNNActorCritic((56, 56, 3), 3)
+    cur = tmp_path / "current.pth"
+    torch.save(ac.state_dict(), cur)
+    pol, use_cnn = load_policy(str(cur), device="cpu")
+    assert use_cnn and not pol.training
+    for a, b in zip(pol.state_dict().values(), ac.state_dict().values()):
+        assert torch.equal(a, b)
+    legacy = {k.replace("actor_extractor.network", "feature_extractor.conv"): v for k, v in ac.state_dict().items()
+              if "critic_extractor" not in k}
+    old = tmp_path / "legacy.pth"
+    torch.save(legacy, old)
+    pol2, _ = load_policy(str(old), device="cpu")
+    sd = pol2.state_dict()
+    assert torch.equal(sd["actor_extractor.network.0.weight"], ac.state_dict()["actor_extractor.network.0.weight"])
+    assert torch.equal(sd["critic_extractor.network.0.weight"], ac.state_dict()["actor_extractor.network.0.weight"])
+    assert torch.equal(sd["actor.2.weight"], ac.state_dict()["actor.2.weight"])
+    mlp = MLPActorCritic(768, 3)
+    m = tmp_path / "mlp.pth"
+    torch.save(mlp.state_dict(), m)
+    pol3, use_cnn3 = load_policy(str(m), device="cpu", obs_shape=(768,))
+    assert not use_cnn3 and torch.equal(pol3.actor[0].weight, mlp.actor[0].weight)
