@@ -4,9 +4,7 @@ stacked-weight policy evaluation FOMAML uses).  Compute entry points must refuse
 from __future__ import annotations
 
 import inspect
-import os
 
-import numpy as np
 import pytest
 import torch
 

@@ -6,7 +6,6 @@ from __future__ import annotations
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -1,4 +1,4 @@
-import torch, time
+import torch
 dev="cuda:0"
 x = torch.empty(10*1024**3, dtype=torch.uint8, device=dev)
 y = torch.empty(5*1024**3, dtype=torch.uint8, device=dev)

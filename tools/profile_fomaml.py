@@ -3,7 +3,7 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "ppo-2dgrid_b200")]
-import numpy as np, torch
+import torch
 from src.fomaml import FOMAML, _stack
 from src.scenario_creator.scenario_creator import ScenarioCreator
 torch.backends.cudnn.benchmark = True

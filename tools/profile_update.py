@@ -24,7 +24,6 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
 
 # A/B: literal conv1 vs blocked conv1, fwd+bwd on one minibatch and fwd on one rollout batch
-import time
 s, a, *_ = agent.buffer.get()
 xs, acts = s.reshape(-1, 56, 56, 3)[:MB], a.reshape(-1)[:MB]
 for blocked in (False, True):
