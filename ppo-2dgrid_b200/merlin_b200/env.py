@@ -52,7 +52,7 @@ class BatchedMerlinEnv:
     def __init__(self, num_envs, cells=None, agent=None, *, enc=None, width=None, height=None, max_steps=None,
                  device="cuda", n_actions=3, auto_reset=True, reset_mode="next", stuck_penalty=False,
                  stuck_max_stay=3, stuck_penalty_value=-0.1, exploration_bonus=0.0, want_symbolic=True,
-                 want_rgb=True, generate=None):
+                 want_rgb=True, generate=None, episode_stats=True):
         """cells: packed u8[L, H*W] (merlin_b200.codes) or `enc`: Grid.encode() arrays u8[L, W, H, 3];
         agent: i32[L, 3] = (x, y, dir).  `reset_mode`: "next" advances each env's pool cursor by num_envs at
         every restart (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
@@ -81,6 +81,9 @@ class BatchedMerlinEnv:
         self.num_envs, self.width, self.height = int(num_envs), int(width), int(height)
         self.n_actions = n_actions
         self.want_symbolic, self.want_rgb = want_symbolic, want_rgb
+        # episode_stats=False: step() skips the optional per-env outputs (episode return / length, stuck, done): the
+        # gymnasium 5-tuple only, 17 bytes less written per env-step
+        self.episode_stats = bool(episode_stats)
         self.auto_reset = auto_reset
 
         self._lib = _lib.load()
@@ -207,7 +210,7 @@ class BatchedMerlinEnv:
         _lib.check(self._lib.merlin_env_step(
             self._h, actions.data_ptr(), obs.data_ptr() if obs is not None else None,
             sym.data_ptr() if sym is not None else None, b.reward.data_ptr(), b.terminated.data_ptr(),
-            b.truncated.data_ptr(), C.byref(b._extras), self._stream()))
+            b.truncated.data_ptr(), C.byref(b._extras) if self.episode_stats else None, self._stream()))
         info = {"episode_return": b.episode_return, "episode_length": b.episode_length, "stuck": b.stuck,
                 "done": b.done, "obs_symbolic": sym}
         return obs, b.reward, b.terminated, b.truncated, info
