@@ -1,0 +1,47 @@
+"""GPU tier: the measurement tools run end to end on tiny configurations and print the JSON they promise."""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _run(args, timeout=600):
+    res = subprocess.run([sys.executable] + args, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    assert res.returncode == 0, res.stderr[-2000:]
+    return res.stdout.strip().splitlines()
+
+
+def test_train_ppo_tool_tiny(tmp_path):
+    ckpt = str(tmp_path / "ppo.pth")
+    lines = _run(["tools/train_ppo.py", "--envs", "64", "--horizon", "8", "--minibatch", "128", "--update-epochs", "1",
+                  "--total-steps", "1024", "--layouts", "256", "--eval-tasks", "4", "--save", ckpt])
+    out = json.loads(lines[-1])
+    assert out["unit"] == "env-steps/s" and out["total_steps"] == 1024 and out["value"] > 0
+    assert out["config"]["obs_storage"] == "symbolic" and os.path.exists(ckpt)
+    lines = _run(["tools/eval_sweep.py", "--ckpt", ckpt, "--difficulty", "medium", "--sizes", "8", "--tasks", "6"])
+    row = json.loads(lines[-1])
+    assert row["tasks"] == 6 and 1 <= row["mean_steps"] <= 256
+
+
+def test_train_fomaml_tool_tiny(tmp_path):
+    lines = _run(["tools/train_fomaml.py", "--iterations", "2", "--tasks-per-batch", "4", "--k-steps", "16", "--warmup", "1"])
+    out = json.loads(lines[-1])
+    assert out["iterations"] == 2 and out["value"] > 0 and len(out["history"]) >= 2
+
+
+def test_bench_tool_small_batch():
+    lines = _run(["bench.py", "--envs", "32768", "--steps", "16", "--warmup", "3", "--layouts", "256", "--skip-cpu-baseline"])
+    assert len(lines) == 1  # ONE JSON line on stdout
+    out = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e"):
+        assert key in out, key
+    assert out["gpu_launches"] == 16 and out["roofline"]["bound"] == "hbm" and out["e2e"]["h2d_bytes_per_step"] == 32768 * 8
