@@ -38,6 +38,9 @@ class FOMAML:
         if not cfg:
             raise ValueError(f"Unknown difficulty: {difficulty}")
         self.size = int({**self.sc.global_cfg, **cfg.get("params", {})}.get("size", 16))
+        if self.sc.obs_cfg.get("fully_observable", False):
+            raise NotImplementedError("task-batched FOMAML consumes the egocentric 56x56x3 frames; the fully observable "
+                                      "grid is served on the single-env path only (ScenarioCreator.create_env)")
         if self.sc.obs_cfg.get("flatten", False):
             self.use_cnn = False
             self.meta_policy = MLPActorCritic(56 * 56 * 3, 3).to(self.device)
