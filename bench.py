@@ -412,6 +412,7 @@ def run_ours(args):
             "value": n / dt, "unit": UNIT, "cores": ref.cores, "kind": "port",
             "sample": f"{n} env-steps ({ref.cores} procs x {per_proc}) in {dt:.1f} s, mediumhard 16x16 random actions, "
                       "literal minigrid-3.0.0 restatement + reference wrapper stack (upstream not installable)",
+            "per_process_value": per_proc / dt,  # one env in one process, the way the reference itself runs
             "c_oracle_value": c_rate, "c_oracle_threads": c_threads,
             "c_oracle_note": "optimised C restatement (OpenMP), not the reference"}
     print(json.dumps(line), flush=True)
