@@ -19,50 +19,60 @@ from src.wrappers.three_action_wrapper import ThreeActionWrapper
 DEFAULT_CONFIG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "scenario.yaml")
 
 
+_PACKAGED_DEFAULT = "src/config/scenario.yaml"
+# attribute <- (top-level YAML key, value when the key is absent); the reference reads the same five sections
+_SECTIONS = (("seed", "seed", 42), ("global_cfg", "global", None), ("obs_cfg", "observation", None),
+             ("rewards_cfg", "rewards", None), ("logging_cfg", "logging", None))
+
+
 class ScenarioCreator:
-    def __init__(self, config_path: str = "src/config/scenario.yaml"):
-        if not os.path.exists(config_path):
-            if config_path == "src/config/scenario.yaml" and os.path.exists(DEFAULT_CONFIG):
-                config_path = DEFAULT_CONFIG  # the packaged table, when not run from the repo root
-            else:
-                raise FileNotFoundError(f"Config not found: {config_path}")
-        with open(config_path, "r") as f:
-            self.config = yaml.safe_load(f)
-        self.seed = self.config.get("seed", 42)
-        self.global_cfg = self.config.get("global", {})
-        self.obs_cfg = self.config.get("observation", {})
-        self.rewards_cfg = self.config.get("rewards", {})
-        self.logging_cfg = self.config.get("logging", {})
+    def __init__(self, config_path: str = _PACKAGED_DEFAULT):
+        path = config_path
+        if not os.path.exists(path) and path == _PACKAGED_DEFAULT and os.path.exists(DEFAULT_CONFIG):
+            path = DEFAULT_CONFIG  # the packaged table, when not run from the repo root
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"Config not found: {config_path}")
+        with open(path) as fh:
+            table = yaml.safe_load(fh)
+        self.config = table
+        for attr, key, missing in _SECTIONS:
+            setattr(self, attr, table.get(key, {} if missing is None else missing))
         self._validate_grid_sizes()
 
     def _validate_grid_sizes(self):
-        sizes = set()
-        for cfg in self.config["difficulties"].values():
-            env_id = cfg["env_id"]
-            if "-" in env_id and "x" in env_id:
-                sizes.add(env_id.split("-")[-2])
-        if len(sizes) > 1:
-            raise ValueError(f"Multiple grid sizes detected: {sizes}")
+        """One table, one grid size: ids shaped like `...-16x16-v0` must agree on the `16x16` part."""
+        seen = []
+        for entry in self.config["difficulties"].values():
+            parts = entry["env_id"].split("-")
+            if len(parts) > 1 and "x" in entry["env_id"] and parts[-2] not in seen:
+                seen.append(parts[-2])
+        if len(seen) > 1:
+            raise ValueError(f"Multiple grid sizes detected: {set(seen)}")
 
     def _difficulty_cfg(self, difficulty):
-        cfg = self.config["difficulties"].get(difficulty)
-        if not cfg:
-            raise ValueError(f"Unknown difficulty: {difficulty}")
-        return cfg
+        entry = self.config["difficulties"].get(difficulty)
+        if entry:
+            return entry
+        raise ValueError(f"Unknown difficulty: {difficulty}")
+
+    def _env_params(self, entry):
+        merged = dict(self.global_cfg)
+        merged.update(entry.get("params", {}))
+        return merged
 
     # ---- the reference's single-env path ----------------------------------------------------------------
     def create_env(self, difficulty: str = "easy", seed=None):
         """`seed` is accepted and ignored, as in the reference (the env is seeded by `reset(seed=...)`)."""
-        cfg = self._difficulty_cfg(difficulty)
-        env = _register.make(cfg["env_id"], **{**self.global_cfg, **cfg.get("params", {})})
-        if self.obs_cfg.get("fully_observable", False):
-            env = FullyObsWrapper(env)
-        else:
-            env = RGBImgPartialObsWrapper(env)
-        env = ImgObsWrapper(env)
+        entry = self._difficulty_cfg(difficulty)
+        full = bool(self.obs_cfg.get("fully_observable", False))
+        stack = [FullyObsWrapper if full else RGBImgPartialObsWrapper, ImgObsWrapper]
         if self.obs_cfg.get("flatten", False):
-            env = FlattenObservation(env)
-        return ThreeActionWrapper(env)
+            stack.append(FlattenObservation)
+        stack.append(ThreeActionWrapper)
+        env = _register.make(entry["env_id"], **self._env_params(entry))
+        for wrap in stack:
+            env = wrap(env)
+        return env
 
     def sample_scenarios(self, n: int = 5, difficulty: str = "easy"):
         return [self.create_env(difficulty) for _ in range(n)]
@@ -80,7 +90,7 @@ class ScenarioCreator:
         from merlin_b200 import layouts as _layouts
 
         cfg = self._difficulty_cfg(difficulty)
-        params = {**self.global_cfg, **cfg.get("params", {})}
+        params = self._env_params(cfg)
         size = int(size if size is not None else params.get("size", 16))
         diff = _register.DIFFICULTY_OF[cfg["env_id"]]
         common = dict(width=size, height=size)
@@ -107,12 +117,12 @@ class ScenarioCreator:
     def get_env_id(self, difficulty: str) -> str:
         return self.config["difficulties"][difficulty]["env_id"]
 
-    def get_logging_params(self) -> dict:
-        return self.logging_cfg
-
     def get_observation_params(self) -> dict:
         return self.obs_cfg
 
+    def get_logging_params(self) -> dict:
+        return self.logging_cfg
+
     def get_env_size_str(self, difficulty: str) -> str:
-        size = self.config["difficulties"][difficulty].get("params", {}).get("size", 16)
-        return f"{size}x{size}"
+        side = self.config["difficulties"][difficulty].get("params", {}).get("size", 16)
+        return "x".join((str(side),) * 2)
