@@ -18,6 +18,8 @@
  *                                 optionally StuckPenaltyWrapper (src/wrappers/stuck_penalty_wrapper.py:29-58)
  *   merlin_env_render             RGBImgPartialObsWrapper.observation on stored symbolic observations (batched,
  *                                 gathered) -- the read side of a compact RolloutBuffer (src/rollout_buffer.py:3-32)
+ *   merlin_env_render_f32         the same, written as the float32 `x / 255.0` tensor CNNFeatureExtractor.forward
+ *                                 consumes (src/actor_critic.py:21), in the blocked layout of its first layer
  *   merlin_gae                    PPO.compute_gae src/ppo.py:107-120 ; FOMAML src/fomaml.py:116-123
  *
  * Conventions
@@ -133,6 +135,15 @@ int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, u
  * block contiguous with channel index c*16 + dy*4 + dx (space-to-depth; what the actor-critic's first layer reads). */
 int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
                       uint8_t* out, int32_t blocked, void* stream);
+
+/* The same frames as the float32 tensor the policy's first layer reads: out: DEVICE f32[m][14][14][48] in the blocked
+ * layout of merlin_env_render(blocked = 1).  normalise = 0: the pixel value 0..255 as float32;  1: pixel / 255.0f (IEEE
+ * float32 division) and 2: pixel * (1.0f / 255.0f) -- the two things `x / 255.0` in CNNFeatureExtractor.forward
+ * (src/actor_critic.py:21) evaluates to, in torch's CPU and CUDA kernels respectively (frames reach it as float32 through
+ * PPO._obs_to_tensor, src/ppo.py:58-62, and RolloutBuffer.states, src/rollout_buffer.py:5).  One 37 632-byte streaming
+ * write per frame instead of a u8 frame plus a cast pass plus a layout copy on the learner's minibatch path. */
+int merlin_env_render_f32(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
+                          float* out, int32_t normalise, void* stream);
 
 /* The fully observable symbolic observation of every env's CURRENT state -- minigrid FullyObsWrapper.observation,
  * which the reference selects with `observation.fully_observable: true` (src/scenario_creator/scenario_creator.py:45-46):

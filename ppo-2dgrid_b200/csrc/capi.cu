@@ -49,6 +49,7 @@ struct merlin_env {
   int n_layouts = 0;
   bool mutable_grid = false;
   bool has_atlas = false;
+  int n_present = kAtlasTiles;           // atlas slots the current layout pool can show (host copy of the popcount)
   bool was_reset = false;
   int64_t launches = 0;
   // device memory
@@ -66,6 +67,12 @@ struct merlin_env {
   uint32_t* tile_present = nullptr;      // [4] device words, rewritten by upload_layouts
   unsigned long long* bad_actions = nullptr;
 };
+
+static int count_present(const uint32_t (&present)[4]) {
+  int n = 0;
+  for (uint32_t w : present) n += __builtin_popcount(w);
+  return n;
+}
 
 static EnvParams base_params(const merlin_env* h) {
   EnvParams p{};
@@ -216,6 +223,7 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
   if (err == cudaSuccess) err = cudaMemcpy(h->pool_agent, agent.data(), agent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMemcpy(h->tile_present, present, sizeof present, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) return cuda_fail(err, "layout upload");
+  h->n_present = count_present(present);
   h->was_reset = false;
   return merlin_env_set_cursors(h, nullptr);
 }
@@ -254,6 +262,7 @@ int merlin_env_generate_layouts(merlin_env_t* h, int32_t difficulty, uint64_t se
   if (h->mutable_grid) present[0] = present[1] = present[2] = present[3] = 0xffffffffu;
   err = cudaMemcpy(h->tile_present, present, sizeof present, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) return cuda_fail(err, "layout generation (mask)");
+  h->n_present = count_present(present);
   h->launches += 1;
   h->was_reset = false;
   return merlin_env_set_cursors(h, nullptr);
@@ -365,6 +374,28 @@ int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, c
   p.sched = h->sched + 2;
   cudaError_t err = launch_render(p, blocked != 0, h->sm_count, static_cast<cudaStream_t>(stream));
   if (err != cudaSuccess) return cuda_fail(err, "render launch");
+  h->launches += 1;
+  return MERLIN_OK;
+}
+
+int merlin_env_render_f32(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, const int64_t* index, int32_t m,
+                          float* out, int32_t normalise, void* stream) {
+  if (!h || !obs_sym || !out) return fail(MERLIN_EINVAL, "merlin_env_render_f32: null argument");
+  if (m < 0 || n_rows < 0) return fail(MERLIN_EINVAL, "merlin_env_render_f32: negative size");
+  if (!h->has_atlas) return fail(MERLIN_ESTATE, "frames requested before the tile atlas was set");
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(MERLIN_EINVAL, "out must be 16-byte aligned");
+  if (normalise < 0 || normalise > 2) return fail(MERLIN_EINVAL, "merlin_env_render_f32: normalise must be 0, 1 or 2");
+  if (!index && n_rows && m > n_rows) return fail(MERLIN_EINVAL, "merlin_env_render_f32: more frames than observation rows");
+  DeviceGuard guard(h->cfg.device);
+  RenderParams p{};
+  p.sym = obs_sym; p.index = index; p.out_f32 = out; p.M = m; p.n_rows = n_rows;
+  p.atlas = h->atlas_blocked;
+  p.tile_present = h->tile_present;
+  p.sched = h->sched + 2;
+  p.normalise = normalise;
+  p.cap_tiles = h->n_present < 8 ? 8 : (h->n_present > kAtlasTiles ? kAtlasTiles : h->n_present);
+  cudaError_t err = launch_render_f32(p, h->sm_count, static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "render_f32 launch");
   h->launches += 1;
   return MERLIN_OK;
 }

@@ -622,6 +622,131 @@ cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cud
 }
 
 // ---------------------------------------------------------------------------------------------------
+// render_f32_kernel: the blocked frame as float32 -- f32[M][14][14][48], optionally pixel / 255.0f -- i.e. the very
+// tensor the actor-critic's first layer reads (reference src/actor_critic.py:21 forms `x / 255.0` from a float32 copy
+// of the frame on every evaluation).  Writing it here replaces three passes of the learner's minibatch path (u8 frame
+// write, u8 read + f32 write of the cast, and the layout copy) by one 37 632-byte streaming write per frame.
+//
+// One warp per frame.  The atlas slots the layout pool can show are converted ONCE per CTA into a float atlas in
+// shared memory (compacted: slot_of_kind[128]; 768 B per staged tile, `cap_tiles` of them), so a 16-byte output chunk
+// is one u16 map read (shared by 4 lanes), one slot read and one 16-byte shared-memory read.  A kind that is not
+// staged (a CUDA graph replayed after a re-upload brought new tile kinds) is converted on the fly from the u8 atlas.
+// HBM-bound: 147 (+8) B read, 37 632 B written per frame.
+constexpr int kF32Chunks = kImgBytes / 4;                  // 2352 float4 chunks per frame
+constexpr int kF32Iters = (kF32Chunks + 31) / 32;          // 74
+constexpr int kRenderF32Group = 8;                          // frames per ticket: 301 KB, like the u8 kernels' groups
+constexpr int kRenderF32Threads = 256;
+
+__host__ __device__ constexpr size_t render_f32_smem(int cap_tiles) {
+  return (size_t)cap_tiles * kTileBytes * 4 + 128 + 592 * 2 + (kRenderF32Threads / 32) * 128;
+}
+
+// normalise: 0 = the pixel value, 1 = pixel / 255.0f (IEEE division: what torch's CPU kernels compute for `x / 255.0`),
+// 2 = pixel * (1.0f / 255.0f) (what torch's CUDA kernel computes for a tensor divided by a Python scalar)
+__device__ __forceinline__ float pixel_f32(uint32_t b, int normalise) {
+  const float v = (float)b;
+  if (normalise == 1) return __fdiv_rn(v, 255.0f);
+  if (normalise == 2) return __fmul_rn(v, __fdiv_rn(1.0f, 255.0f));
+  return v;
+}
+
+__global__ void __launch_bounds__(kRenderF32Threads, 3) render_f32_kernel(const RenderParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int warps_per_cta = kRenderF32Threads / 32;
+  float* atlas_f = reinterpret_cast<float*>(smem);
+  uint8_t* slot_s = smem + (size_t)p.cap_tiles * kTileBytes * 4;
+  uint16_t* map_s = reinterpret_cast<uint16_t*>(slot_s + 128);
+  uint8_t* kp = reinterpret_cast<uint8_t*>(map_s + 592) + warp * 128;   // [0..48] slots, [64..112] kinds
+  const int normalise = p.normalise;
+
+  if (threadIdx.x < kAtlasTiles) {  // compact the present tiles: slot = number of present tiles below this one
+    const int t = threadIdx.x;
+    int below = 0;
+    for (int w = 0; w < (t >> 5); ++w) below += __popc(__ldg(p.tile_present + w));
+    below += __popc(__ldg(p.tile_present + (t >> 5)) & ((1u << (t & 31)) - 1u));
+    slot_s[t] = (tile_bit(p.tile_present, t) && below < p.cap_tiles) ? (uint8_t)below : (uint8_t)255;
+  }
+  for (int c = threadIdx.x; c < kChunks; c += blockDim.x) map_s[c] = (uint16_t)chunk_lut_blocked(c);
+  __syncthreads();
+  for (int t = warp; t < kAtlasTiles; t += warps_per_cta) {
+    const uint32_t slot = slot_s[t];
+    if (slot == 255) continue;
+    for (int i = lane; i < kTileBytes; i += 32)
+      atlas_f[slot * kTileBytes + i] = pixel_f32(__ldg(p.atlas + t * kTileBytes + i), normalise);
+  }
+  __syncthreads();
+
+  __shared__ int s_next;
+  const int n_groups = (p.M + kRenderF32Group - 1) / kRenderF32Group;
+  if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+  __syncthreads();
+  int group = s_next;
+  while (group < n_groups) {
+    __syncthreads();  // everyone has read the ticket
+    if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+    for (int m = group * kRenderF32Group + warp; m < min(p.M, (group + 1) * kRenderF32Group); m += warps_per_cta) {
+      long long row = p.index ? p.index[m] : m;
+      if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;
+      const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < kCells) {
+          const uint32_t kind = kind_of_sym(sym[3 * k], sym[3 * k + 1], sym[3 * k + 2], k == (kView / 2) * kView + (kView - 1));
+          kp[k] = slot_s[kind];
+          kp[64 + k] = (uint8_t)kind;
+        }
+      }
+      __syncwarp();
+      float* frame = p.out_f32 + (size_t)m * kImgBytes;
+#pragma unroll 4
+      for (int k = 0; k < kF32Iters; ++k) {
+        const int f = lane + 32 * k;
+        if (f < kF32Chunks) {
+          const uint32_t q = map_s[f >> 2];
+          const uint32_t cell = q & 0xff, off = (q >> 8) * 16 + (f & 3) * 4;   // element offset inside the tile
+          const uint32_t slot = kp[cell];
+          float4 v;
+          if (slot != 255) {
+            v = *reinterpret_cast<const float4*>(atlas_f + slot * kTileBytes + off);
+          } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.atlas + (uint32_t)kp[64 + cell] * kTileBytes + off));
+            v = make_float4(pixel_f32(w & 0xff, normalise), pixel_f32((w >> 8) & 0xff, normalise),
+                            pixel_f32((w >> 16) & 0xff, normalise), pixel_f32(w >> 24, normalise));
+          }
+          st_stream_v4(frame + f * 4, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        }
+      }
+      __syncwarp();  // kp is reused by this warp's next frame
+    }
+    __syncthreads();  // the next ticket is in shared memory
+    group = s_next;
+  }
+  if (threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+  }
+}
+
+cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t stream) {
+  if (p.M <= 0) return cudaSuccess;
+  const size_t smem = render_f32_smem(p.cap_tiles);
+  static bool big_smem_ok = false;  // > 48 KB of dynamic shared memory (every atlas slot staged) is opt-in
+  if (smem > 48 * 1024 && !big_smem_ok) {
+    cudaError_t err = cudaFuncSetAttribute(render_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)render_f32_smem(kAtlasTiles));
+    if (err != cudaSuccess) return err;
+    big_smem_ok = true;
+  }
+  const int per_sm = smem > 72 * 1024 ? 2 : 3;
+  const int grid = min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
+  render_f32_kernel<<<grid, kRenderF32Threads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // full_obs_kernel: the fully observable symbolic observation (minigrid FullyObsWrapper; selected by
 // `observation.fully_observable: true` in the reference's scenario.yaml, src/scenario_creator/scenario_creator.py:45-46).
 // One thread per output cell, output-order indexing (coalesced 3-byte cells; the 256-byte grids are read through L1).

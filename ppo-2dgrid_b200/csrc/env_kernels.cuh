@@ -74,8 +74,13 @@ struct RenderParams {
   unsigned* sched;           // [2] in-order ticket counter + finished-CTA counter (self-resetting)
   int M;
   long long n_rows;          // rows of `sym` (index bound), 0 = unchecked
+  // float32 variant only (launch_render_f32): blocked layout, `atlas` = the blocked u8 atlas
+  float* out_f32;            // [M][14][14][48]
+  int normalise;             // 0: the pixel value; 1: pixel / 255.0f (IEEE division); 2: pixel * (1.0f / 255.0f)
+  int cap_tiles;             // atlas slots the float atlas in shared memory can hold (8..128)
 };
 cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream);
+cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t stream);
 // On-device layout generation (layout_kernels.cu): fills pool slots first_slot .. first_slot+count-1 with layouts number
 // first_number .. of the stream `seed`; difficulty 0 easy, 1 medium, 2 mediumhard, 3 hard, 4 hardest.
 cudaError_t launch_layouts(uint8_t* pool_cells, uint32_t* pool_agent, int cell_stride, int W, int H, int difficulty,

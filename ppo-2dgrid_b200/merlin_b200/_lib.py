@@ -20,7 +20,7 @@ EXPORTS = (
     "merlin_env_generate_layouts", "merlin_env_read_layouts", "merlin_env_layout_count",
     "merlin_env_set_tile_atlas", "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step",
     "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
-    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_env_render", "merlin_env_full_obs", "merlin_gae",
+    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_env_render", "merlin_env_render_f32", "merlin_env_full_obs", "merlin_gae",
     "merlin_pack_cell", "merlin_last_error", "merlin_version",
 )
 
@@ -74,6 +74,8 @@ def load():
     lib.merlin_env_full_obs.restype = C.c_int
     lib.merlin_env_render.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
     lib.merlin_env_render.restype = C.c_int
+    lib.merlin_env_render_f32.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
+    lib.merlin_env_render_f32.restype = C.c_int
     lib.merlin_env_step_kernel.argtypes = [vp, C.c_int]
     lib.merlin_env_step_kernel.restype = C.c_char_p
     lib.merlin_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp]

@@ -226,14 +226,26 @@ class BatchedMerlinEnv:
         _lib.check(self._lib.merlin_env_full_obs(self._h, out.data_ptr(), self._stream()))
         return out
 
-    def render(self, obs_symbolic, index=None, out=None, blocked=False):
+    def render(self, obs_symbolic, index=None, out=None, blocked=False, dtype=torch.uint8, normalise=False):
         """Frames from stored symbolic observations: `obs_symbolic` u8[R, 7, 7, 3] (any leading shape, contiguous),
         `index` optional int64[M] rows to render (a minibatch gather fused with the rendering).
         Returns u8[M, 56, 56, 3] (bit-identical to what `step` wrote for those states) or, with `blocked=True`,
-        u8[M, 14, 14, 48] (4x4 pixel blocks, channel-major: the actor-critic's space-to-depth input)."""
+        u8[M, 14, 14, 48] (4x4 pixel blocks, channel-major: the actor-critic's space-to-depth input).
+        `dtype=torch.float32` (blocked only): f32[M, 14, 14, 48] holding the pixel values 0..255 (what
+        CNNActorCritic takes) or the reference's `x / 255.0` (src/actor_critic.py:21): `normalise="divide"` (or True)
+        = IEEE division, torch's CPU result; `normalise="reciprocal"` = x * (1/255), torch's CUDA result -- the
+        first layer's input tensor written by the kernel itself, no cast or layout pass afterwards."""
         sym = obs_symbolic
         if sym.dtype != torch.uint8 or sym.device != self.device or not sym.is_contiguous():
             raise ValueError("obs_symbolic must be a contiguous uint8 tensor on the env's device")
+        if dtype not in (torch.uint8, torch.float32):
+            raise ValueError("dtype must be torch.uint8 or torch.float32")
+        modes = {False: 0, None: 0, "none": 0, True: 1, "divide": 1, "reciprocal": 2}
+        if normalise not in modes:
+            raise ValueError("normalise must be False, True / 'divide' or 'reciprocal'")
+        as_f32 = dtype == torch.float32
+        if as_f32 and not blocked:
+            raise ValueError("float32 frames are written in the blocked layout only (blocked=True)")
         rows = sym.numel() // (VIEW * VIEW * 3)
         if index is not None:
             if index.dtype != torch.int64 or index.device != self.device or not index.is_contiguous():
@@ -243,13 +255,19 @@ class BatchedMerlinEnv:
             m = rows
         shape = (m, 2 * VIEW, 2 * VIEW, 48) if blocked else (m,) + OBS_SHAPE
         if out is None:
-            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
-        elif out.numel() != m * VIEW * TILE * VIEW * TILE * 3 or out.dtype != torch.uint8 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous uint8 tensor of m * 9408 bytes")
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        elif (out.numel() != m * VIEW * TILE * VIEW * TILE * 3 or out.dtype != dtype or not out.is_contiguous()
+              or out.device != self.device):
+            raise ValueError(f"out must be a contiguous {dtype} tensor of m * 9408 elements on the env's device")
         if m == 0:
             return out
-        _lib.check(self._lib.merlin_env_render(self._h, sym.data_ptr(), rows, index.data_ptr() if index is not None else None,
-                                               m, out.data_ptr(), 1 if blocked else 0, self._stream()))
+        idx_ptr = index.data_ptr() if index is not None else None
+        if as_f32:
+            _lib.check(self._lib.merlin_env_render_f32(self._h, sym.data_ptr(), rows, idx_ptr, m, out.data_ptr(),
+                                                       modes[normalise], self._stream()))
+        else:
+            _lib.check(self._lib.merlin_env_render(self._h, sym.data_ptr(), rows, idx_ptr, m, out.data_ptr(),
+                                                   1 if blocked else 0, self._stream()))
         return out
 
     # ---- state views (synchronous host copies; debugging / tests / gym adapter) ------------------

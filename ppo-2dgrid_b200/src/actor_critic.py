@@ -49,9 +49,10 @@ class CNNFeatureExtractor(nn.Module):
         return self.network(x / 255.0)
 
     def forward_blocked(self, xb):
-        """Same function on `space_to_depth4` input.  The first layer (8x8, stride 4, 3 input channels) is evaluated
-        as a 2x2 stride-1 convolution over 48 channels with the SAME parameters (re-indexed on the fly, 1/255 folded
-        into them): identical sums in a different order, and a shape cuDNN runs several times faster than C = 3."""
+        """Same function on `space_to_depth4` input (float pixel values 0..255).  The first layer (8x8, stride 4, 3
+        input channels) is evaluated as a 2x2 stride-1 convolution over 48 channels with the SAME parameters
+        (re-indexed on the fly, 1/255 folded into them): identical sums in a different order, and a shape cuDNN runs
+        several times faster than C = 3."""
         conv1 = self.network[0]
         h = torch.nn.functional.conv2d(xb, _space_to_depth4_weight(conv1.weight) * (1.0 / 255.0), conv1.bias)
         return self.network[1:](h)
@@ -104,8 +105,11 @@ class CNNActorCritic(_ActorCriticBase):
 
     def _logits_value(self, obs):
         if obs.ndim == 4 and obs.shape[-1] == 48:
-            # frames already in the blocked layout u8[N, H/4, W/4, 48] (BatchedMerlinEnv.render(..., blocked=True))
-            xb = obs.permute(0, 3, 1, 2).float()
+            # frames already in the blocked layout [N, H/4, W/4, 48] (BatchedMerlinEnv.render(..., blocked=True)), pixel
+            # values 0..255 as uint8 or -- written by the render kernel itself, nothing to cast or copy here -- float32
+            xb = obs.permute(0, 3, 1, 2)
+            if xb.dtype != torch.float32:
+                xb = xb.float()
             fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
         elif self.blocked_first_layer and obs.ndim == 4 and obs.shape[-1] == 3:
             xb = space_to_depth4(obs)  # shared by both trunks

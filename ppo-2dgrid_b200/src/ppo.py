@@ -28,7 +28,7 @@ from .rollout_buffer import RolloutBuffer
 class PPO:
     def __init__(self, env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
                  minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False,
-                 obs_storage="rgb", amp_dtype=None):
+                 obs_storage="rgb", amp_dtype=None, minibatch_frames=torch.float32):
         self.env = env
         self.batched = isinstance(env, BatchedMerlinEnv)
         self.device = env.device if self.batched else torch.device(device)
@@ -37,6 +37,12 @@ class PPO:
         self.vf_coef, self.ent_coef = vf_coef, ent_coef
         # optional reduced-precision policy evaluation in the update (torch.autocast); None = fp32 like the reference
         self.amp_dtype = amp_dtype
+        # obs_storage='symbolic' only: what the render kernel hands the policy for a minibatch -- the first layer's
+        # float32 input tensor itself (default; same values, so the same update bit for bit), or blocked uint8 pixels
+        # that PyTorch casts afterwards
+        if minibatch_frames not in (torch.float32, torch.uint8):
+            raise ValueError("minibatch_frames must be torch.float32 or torch.uint8")
+        self.minibatch_frames = minibatch_frames
 
         if obs_storage not in ("rgb", "symbolic"):
             raise ValueError("obs_storage must be 'rgb' (56x56x3 frames in the rollout) or 'symbolic' (7x7x3, expanded on read)")
@@ -75,8 +81,8 @@ class PPO:
             self._last_obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=self.device)
             if self.obs_storage == "symbolic":
                 self._last_sym = torch.zeros((N, 7, 7, 3), dtype=torch.uint8, device=self.device)
-                self._mb_frames = torch.zeros((min(self.minibatch_size, self.batch_size), 14, 14, 48), dtype=torch.uint8,
-                                              device=self.device)
+                self._mb_frames = torch.zeros((min(self.minibatch_size, self.batch_size), 14, 14, 48),
+                                              dtype=self.minibatch_frames, device=self.device)
             self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
             self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
             self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
@@ -187,7 +193,8 @@ class PPO:
             stored = states.reshape(n, 7, 7, 3)
 
             def frames(mb):  # minibatch gather + rendering in one kernel
-                return self.env.render(stored, mb, out=self._mb_frames[: mb.numel()], blocked=True)
+                return self.env.render(stored, mb, out=self._mb_frames[: mb.numel()], blocked=True,
+                                       dtype=self.minibatch_frames, normalise=False)
         else:
             stored = states.reshape((n,) + self.obs_shape)
 

@@ -382,6 +382,59 @@ def test_render_from_symbolic_is_bit_identical_to_step_frames(n_actions):
     with pytest.raises(ValueError):
         env.render(sym_store.float())
     assert env.render(sym_store[:0]).shape == (0, 56, 56, 3)
+    # float32 frames (merlin_env_render_f32): the blocked layout as pixel values, or as the `x / 255.0` of the reference's
+    # CNNFeatureExtractor.forward (src/actor_critic.py:21) -- bit-identical to torch's CPU kernel (IEEE division) and
+    # to torch's CUDA kernel (multiplication by 1/255) respectively
+    want_px = torch.as_tensor(_blocked_of(_np(flat_rgb[idx]))).float()
+    f_norm = env.render(sym_store, idx, blocked=True, dtype=torch.float32, normalise=True)
+    assert f_norm.dtype == torch.float32 and f_norm.shape == (1000, 14, 14, 48)
+    assert torch.equal(f_norm.cpu(), want_px / 255.0)
+    want_px = want_px.cuda()
+    assert torch.equal(env.render(sym_store, idx, blocked=True, dtype=torch.float32, normalise="reciprocal"), want_px / 255.0)
+    with pytest.raises(ValueError):
+        env.render(sym_store, idx, blocked=True, dtype=torch.float32, normalise="half")
+    assert torch.equal(env.render(sym_store, idx, blocked=True, dtype=torch.float32), want_px)
+    f_all = env.render(sym_store, blocked=True, dtype=torch.float32, normalise=True)  # all rows, ragged last group
+    assert torch.equal(f_all.cpu(), torch.as_tensor(_blocked_of(_np(flat_rgb))).float() / 255.0)
+    guard = torch.full((5 * 9408 + 64,), -7.0, device="cuda:0")
+    env.render(sym_store, idx[:5], out=guard[32:32 + 5 * 9408].view(5, 14, 14, 48), blocked=True, dtype=torch.float32,
+               normalise=True)
+    assert bool((guard[:32] == -7.0).all()) and bool((guard[-32:] == -7.0).all())
+    assert torch.equal(guard[32:-32].view(5, 14, 14, 48), f_norm[:5])
+    with pytest.raises(ValueError):
+        env.render(sym_store, dtype=torch.float32)  # float32 exists in the blocked layout only
+    assert env.render(sym_store[:0], blocked=True, dtype=torch.float32).shape == (0, 14, 14, 48)
+
+
+def test_render_f32_replayed_from_a_graph_after_the_pool_gained_tile_kinds():
+    """A CUDA graph captured while the layout pool shows 5 tile kinds stays correct after an equal-sized re-upload
+    brings kinds the kernel's float atlas was not sized for (they are converted on the fly from the u8 atlas)."""
+    _, codes, _, layouts, _ = _mods()
+    rng = np.random.default_rng(5)
+    cells, agent = layouts.generate("mediumhard", 11, range(32))
+    env = _make_gpu_env(64, codes.unpack_to_encoding(cells, 11, 11), agent, max_steps=12)
+    sym = torch.zeros((64, 7, 7, 3), dtype=torch.uint8, device="cuda:0")
+    rgb = torch.zeros((64, 56, 56, 3), dtype=torch.uint8, device="cuda:0")
+    out = torch.zeros((64, 14, 14, 48), dtype=torch.float32, device="cuda:0")
+    env.reset(out_obs=rgb, out_symbolic=sym)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        env.render(sym, out=out, blocked=True, dtype=torch.float32, normalise=True)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.render(sym, out=out, blocked=True, dtype=torch.float32, normalise=True)
+    g.replay()
+    assert torch.equal(out.cpu(), torch.as_tensor(_blocked_of(_np(rgb))).float() / 255.0)
+    enc2, agent2 = _object_layouts(rng, 32, 11)  # lava, floor, doors, keys, balls, boxes: 13 more tile kinds
+    env.upload_layouts(codes.pack_encoding(enc2), agent2)
+    env.reset(out_obs=rgb, out_symbolic=sym)
+    for _ in range(6):
+        env.step(torch.as_tensor(rng.integers(0, 3, 64), device="cuda:0"), out_obs=rgb, out_symbolic=sym)
+    assert len(np.unique(_np(sym)[..., 0])) > 5
+    g.replay()
+    assert torch.equal(out.cpu(), torch.as_tensor(_blocked_of(_np(rgb))).float() / 255.0)
 
 
 @pytest.mark.parametrize("N", [1, 33, 257, 5000, 9473])

@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--obs-storage", choices=["rgb", "symbolic"], default="symbolic",
                     help="rollout keeps 56x56x3 frames, or the 7x7x3 symbolic image rendered on read (64x smaller)")
+    ap.add_argument("--mb-frames", choices=["f32", "u8"], default="f32",
+                    help="symbolic storage: the render kernel writes minibatches as the normalised float32 first-layer input "
+                         "(default) or as blocked uint8 pixels that PyTorch casts afterwards")
     ap.add_argument("--cpu-baseline", action="store_true",
                     help="also time one reference-style PPO iteration (N=1, 2048 steps) on the host cores (oracle port)")
     ap.add_argument("--out", default=None)
@@ -96,7 +99,8 @@ def main():
     agent = PPO(env, lr=a.lr, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=a.update_epochs,
                 batch_size=a.envs * a.horizon, minibatch_size=a.minibatch, vf_coef=0.5, ent_coef=a.ent_coef,
                 use_cuda_graph=not a.no_graph, obs_storage=a.obs_storage,
-                amp_dtype=torch.bfloat16 if a.amp == "bf16" else None)
+                amp_dtype=torch.bfloat16 if a.amp == "bf16" else None,
+                minibatch_frames=torch.float32 if a.mb_frames == "f32" else torch.uint8)
 
     def sync():
         if world > 1:
@@ -141,6 +145,7 @@ def main():
                "config": {"workload": f"configs[2]: PPO {a.difficulty} 16x16, {a.envs} envs/GPU x horizon {a.horizon}",
                           "minibatch": a.minibatch, "update_epochs": a.update_epochs, "lr": a.lr, "ent_coef": a.ent_coef,
                           "cuda_graph_rollout": not a.no_graph, "obs_storage": a.obs_storage,
+                          "minibatch_frames": a.mb_frames if a.obs_storage == "symbolic" else None,
                           "rollout_obs_bytes": int(agent.buffer.states.numel() * agent.buffer.states.element_size()),
                           "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "layout_pool_per_gpu": per_rank,
                           "layout_source": "device" if a.device_layouts else "host (reference seeds)", "layout_setup_s": t_lay, "dtype": "fp32 policy (PyTorch defaults: TF32 convolutions" + (", TF32 linear layers" if a.tf32_matmul else ", fp32 linear layers") + ")" + (", bf16 autocast in the update" if a.amp == "bf16" else "") + ", u8 frames", "seed": a.seed},
