@@ -160,8 +160,9 @@ int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float
 int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count); /* synchronises the device */
 int64_t merlin_env_launch_count(merlin_env_t* h);             /* kernels launched so far by this handle */
 /* Tuning/testing knob, process-wide: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
- * 3 = CTA-tile kernel, 5 = symbolic-only kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL).
- * All kernels produce identical results for the outputs they write. */
+ * 3 = CTA-tile kernel, 4 = CTA-tile kernel with the frames stored by the TMA unit (cp.async.bulk), 5 = symbolic-only
+ * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out.
+ * All kernels produce identical results for the outputs they write; "automatic" never picks 4 or 6 (measured slower). */
 int merlin_set_kernel_choice(int choice);
 /* Name of the kernel merlin_env_step launches for this handle (rgb != 0: with an RGB observation). */
 const char* merlin_env_step_kernel(merlin_env_t* h, int rgb);

@@ -453,7 +453,8 @@ const char* merlin_env_step_kernel(merlin_env_t* h, int rgb) {
 }
 
 int merlin_set_kernel_choice(int choice) {
-  if (choice < 0 || choice > 5 || choice == 4) return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile) or 5 (symbolic-only)");
+  if (choice < 0 || choice > 6)
+    return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile), 4 (tile, TMA frame stores), 5 (symbolic-only) or 6 (ordered groups)");
   set_kernel_choice(choice);
   return MERLIN_OK;
 }

@@ -269,6 +269,63 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// env_kernel_ordered<G, STEP, THREADS, MINB>: env_kernel's mapping (a warp owns G consecutive envs for both phases)
+// with the groups handed out IN ORDER, one ticket per warp, from the same self-resetting counter the tile kernel
+// uses.  Every warp of the SM runs its own state phase (no warp-0 bottleneck, no CTA barrier in the loop): the
+// dependent-load chain of a state phase (~10 us) is hidden by all resident warps instead of one per CTA, while the
+// write fronts still advance together.  The next ticket is drawn before the work so its latency is off the path.
+// MEASURED AND NOT ADOPTED (B200, 1M envs, RGB, fraction of the HBM copy peak; env_kernel_tile<16>: 1.08):
+//   G=8, 128 thr x 3 CTAs  1.046    G=16, 128 x 3  1.045    G=32, 128 x 3  1.041    G=8, 128 x 4 (spills)  1.033
+//   G=8, 256 x 2  1.034    G=16, 256 x 2  1.024    G=16, 128 x 4  1.021    G=4, 128 x 4  0.920
+// i.e. in-order hand-out lifts the group mapping from 0.92 (static assignment) to 1.05, but more concurrent state phases
+// buy nothing over the tile kernel: its limit is the store stream, not the state-phase chain.  Kept selectable (choice 6).
+template <int G, bool STEP, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) env_kernel_ordered(const EnvParams p, const int n_groups) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const Flags f(p);
+  uint8_t* atlas_s = smem;
+  uint8_t* warp_s = smem + kAtlasBytes + warp * warp_smem_bytes(G);
+  uint8_t* kinds_s = warp_s;
+  uint8_t* sym_s = warp_s + G * kKindStride;
+
+  uint32_t lut[kChunksPerLane];
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    load_lut(p, lane, lut);
+  }
+  __syncthreads();
+
+  int g = 0;
+  if (lane == 0) g = (int)atomicAdd(&p.sched[0], 1u);
+  g = __shfl_sync(0xffffffffu, g, 0);
+  while (g < n_groups) {
+    int next = 0;
+    if (lane == 0) next = (int)atomicAdd(&p.sched[0], 1u);
+    const int e0 = g * G;
+    const unsigned render_mask = state_phase<G, STEP>(p, f, e0, lane, kinds_s, sym_s);
+    if (f.want_sym && render_mask)
+      emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(G, p.N - e0), render_mask, lane, 32);
+    if (f.want_rgb) {
+      unsigned m = render_mask;
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        blit_frame(atlas_s, kinds_s + i * kKindStride, lut, p.obs_rgb + (size_t)(e0 + i) * kImgBytes, lane);
+      }
+    }
+    __syncwarp();  // smem rows are reused by the next group
+    g = __shfl_sync(0xffffffffu, next, 0);
+  }
+  // every warp of the grid has drawn its last ticket once all of them have passed here: the last one rearms
+  if (lane == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x * (THREADS / 32) - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // env_kernel_tile<T, STEP>: a CTA owns a tile of T <= 32 consecutive envs; warp 0 runs the state phase, every
 // warp of the CTA takes frames of the tile; co-resident CTAs overlap one tile's state phase with others' frames.
 // Shape (B200, 1M envs, RGB), all with tiles handed out in order (see the ticket scheduler below):
@@ -338,6 +395,111 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams
   }
   if (threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
     p.sched[0] = 0;  // every CTA has drawn its last ticket: safe to rearm
+    p.sched[1] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF>: env_kernel_tile with the frame phase routed through the TMA unit.
+// A warp assembles a frame in one of its NBUF shared-memory staging buffers (the same atlas reads, 16-byte shared
+// stores instead of global ones), makes it visible to the async proxy and ONE lane issues a single 9408-byte
+// cp.async.bulk.global.shared::cta for it; the buffer is reused once its bulk group has been read.  The copy engine
+// streams whole frames to HBM while warp 0 is already in the next tile's state phase, and the LSU no longer carries
+// the 10 GB/launch store stream (ncu on env_kernel_tile: L1/TEX 78 % busy next to 85 % DRAM).
+// MEASURED AND NOT ADOPTED (B200, 1M envs, RGB, fraction of the HBM copy peak; env_kernel_tile<16>: 1.08):
+//   T=32, 128 thr x 3 CTAs, 1 buffer/warp  0.96      T=32, 128 x 2, 2 buffers  0.87      T=16, 128 x 3, 1 buffer  0.82
+//   T=32, 256 x 2, 1 buffer  0.82    T=16, 64 x 3, 2 buffers  0.78    T=16, 128 x 2, 2 buffers  0.70    T=16, 256 x 1, 2 buffers  0.48
+// The copy engine itself is not the problem -- tools/cuda/tma_store_bench.cu streams staged frames at 7.56-7.60 TB/s
+// with as little as ONE 64-thread CTA per SM (per-lane st.global.cs.v4: 7.49) -- but every frame byte now crosses
+// shared memory three times (atlas read, staging write, engine read) instead of once, and the staging buffers
+// (9.4 KB per frame in flight) cost a resident CTA per SM.  Kept selectable (kernel choice 4) with its parity tests.
+__device__ __forceinline__ void bulk_store_frame(uint8_t* gdst, const uint8_t* ssrc) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "n"(kImgBytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+
+// Frame phase into shared memory: `stage` receives the frame exactly as blit_frame would write it to global memory.
+__device__ __forceinline__ void blit_frame_smem(const uint8_t* atlas_s, const uint8_t* kp, const uint32_t (&lut)[kChunksPerLane],
+                                                uint8_t* stage, int lane) {
+  const uint2* atlas64 = reinterpret_cast<const uint2*>(atlas_s);
+#pragma unroll
+  for (int k = 0; k < kChunksPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < kChunks) {
+      const uint32_t q = lut[k];
+      const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
+      const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
+      const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];
+      *reinterpret_cast<uint4*>(stage + c * 16) = make_uint4(a.x, a.y, b.x, b.y);
+    }
+  }
+}
+
+__host__ __device__ constexpr int tile_tma_smem_bytes(int T, int threads, int nbuf) {
+  return tile_smem_bytes(T) + (threads / 32) * nbuf * kImgBytes;
+}
+
+template <int T, bool STEP, int THREADS, int MINB, int NBUF>
+__global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile_tma(const EnvParams p, const int n_tiles) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int warps_per_cta = THREADS / 32;
+  const Flags f(p);
+  uint8_t* atlas_s = smem;
+  uint8_t* kinds_s = smem + kAtlasBytes;
+  uint8_t* sym_s = kinds_s + T * kKindStride;
+  unsigned* mask_s = reinterpret_cast<unsigned*>(smem + tile_smem_bytes(T) - 16);
+  uint8_t* stage_s = smem + tile_smem_bytes(T) + warp * NBUF * kImgBytes;   // this warp's NBUF frame buffers
+
+  uint32_t lut[kChunksPerLane];
+  if (f.want_rgb) {
+    stage_atlas(p, atlas_s);
+    load_lut(p, lane, lut);
+  }
+  int buf = 0;
+  __shared__ int s_next;
+  if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
+  __syncthreads();
+  int tile = s_next;
+  while (tile < n_tiles) {
+    const int e0 = tile * T;
+    if (warp == 0) {
+      const unsigned m = state_phase<T, STEP>(p, f, e0, lane, kinds_s, sym_s);
+      if (lane == 0) *mask_s = m;
+    } else if (threadIdx.x == 32) {
+      s_next = (int)atomicAdd(&p.sched[0], 1u);
+    }
+    __syncthreads();
+    const unsigned render_mask = *mask_s;
+    const int next = s_next;
+    if (f.want_sym && render_mask)
+      emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(T, p.N - e0), render_mask, threadIdx.x, blockDim.x);
+    if (f.want_rgb) {
+      for (int i = warp; i < T; i += warps_per_cta) {
+        if (!((render_mask >> i) & 1)) continue;
+        uint8_t* stage = stage_s + buf * kImgBytes;
+        if (lane == 0) bulk_wait_read<NBUF - 1>();   // the bulk group that last read this buffer is done with it
+        __syncwarp();
+        blit_frame_smem(atlas_s, kinds_s + i * kKindStride, lut, stage, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+        __syncwarp();
+        if (lane == 0) bulk_store_frame(p.obs_rgb + (size_t)(e0 + i) * kImgBytes, stage);
+        buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+      }
+    }
+    __syncthreads();
+    tile = next;
+  }
+  if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the engine's reads
+  if (threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+    p.sched[0] = 0;
     p.sched[1] = 0;
   }
 }
@@ -733,12 +895,10 @@ __global__ void __launch_bounds__(kRenderF32Threads, 3) render_f32_kernel(const 
 cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
   const size_t smem = render_f32_smem(p.cap_tiles);
-  static bool big_smem_ok = false;  // > 48 KB of dynamic shared memory (every atlas slot staged) is opt-in
-  if (smem > 48 * 1024 && !big_smem_ok) {
+  if (smem > 48 * 1024) {  // every atlas slot staged (7-action handles): opt in, per device (the call is cheap)
     cudaError_t err = cudaFuncSetAttribute(render_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)render_f32_smem(kAtlasTiles));
     if (err != cudaSuccess) return err;
-    big_smem_ok = true;
   }
   const int per_sm = smem > 72 * 1024 ? 2 : 3;
   const int grid = min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
@@ -825,6 +985,50 @@ static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStre
   return cudaGetLastError();
 }
 
+#ifndef MERLIN_ORD_G
+#define MERLIN_ORD_G 8
+#define MERLIN_ORD_THREADS 128
+#define MERLIN_ORD_CTAS 3
+#endif
+template <int G, bool STEP, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
+static cudaError_t launch_ordered_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  constexpr int warps = THREADS / 32;
+  const int n_groups = (p.N + G - 1) / G;
+  const size_t smem = kAtlasBytes + warps * warp_smem_bytes(G);
+  static int blocks_per_sm_dev[64] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  if (!blocks_per_sm) {
+    cudaError_t err = resident_ctas(env_kernel_ordered<G, STEP, THREADS, MINB>, THREADS, smem, blocks_per_sm);
+    if (err != cudaSuccess) return err;
+    if (MINB < blocks_per_sm) blocks_per_sm = MINB;
+  }
+  const int grid = min(sm_count * blocks_per_sm, (n_groups + warps - 1) / warps);
+  env_kernel_ordered<G, STEP, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p, n_groups);
+  return cudaGetLastError();
+}
+
+#ifndef MERLIN_TMA_T
+#define MERLIN_TMA_T 32
+#define MERLIN_TMA_THREADS 128
+#define MERLIN_TMA_CTAS 3
+#define MERLIN_TMA_NBUF 1
+#endif
+template <int T, bool STEP, int THREADS = MERLIN_TMA_THREADS, int MINB = MERLIN_TMA_CTAS, int NBUF = MERLIN_TMA_NBUF>
+static cudaError_t launch_tile_tma_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  const int n_tiles = (p.N + T - 1) / T;
+  const size_t smem = tile_tma_smem_bytes(T, THREADS, NBUF);
+  static int blocks_per_sm_dev[64] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  if (!blocks_per_sm) {
+    cudaError_t err = resident_ctas(env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF>, THREADS, smem, blocks_per_sm);
+    if (err != cudaSuccess) return err;
+    if (MINB < blocks_per_sm) blocks_per_sm = MINB;
+  }
+  const int grid = min(sm_count * blocks_per_sm, n_tiles);
+  env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF><<<grid, THREADS, smem, stream>>>(p, n_tiles);
+  return cudaGetLastError();
+}
+
 template <bool STEP>
 static cudaError_t launch_warp_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
   constexpr int warps = kWarpKernelThreads / 32;
@@ -853,6 +1057,11 @@ static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t s
   }
   if (choice == 2) return launch_warp_kernel<STEP>(p, sm_count, stream);
   if (choice == 5) return launch_sym_kernel<STEP>(p, stream);
+  if (choice == 6) return launch_ordered_kernel<MERLIN_ORD_G, STEP>(p, sm_count, stream);
+  if (choice == 4) {
+    if ((reinterpret_cast<uintptr_t>(p.obs_rgb) & 15) == 0) return launch_tile_tma_kernel<MERLIN_TMA_T, STEP>(p, sm_count, stream);
+    choice = 3;  // bulk copies need a 16-byte aligned destination
+  }
   if (choice == 3) {
     // tiles of 16 envs once every resident CTA gets one; smaller tiles spread a small batch over more CTAs
     if (p.N >= sm_count * kTileCtasPerSm * 16) return launch_tile_kernel<16, STEP>(p, sm_count, stream);
@@ -871,6 +1080,8 @@ const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
   if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 5;
   if (choice == 5) return "merlin::env_kernel_sym<true>";
   if (choice == 2) return "merlin::env_kernel_warp<true>";
+  if (choice == 4) return "merlin::env_kernel_tile_tma<true>";
+  if (choice == 6) return "merlin::env_kernel_ordered<true>";
   if (choice == 3)
     return n_envs >= sm_count * kTileCtasPerSm * 16 ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>";
   const long long want_warps = (long long)sm_count * 8;

@@ -55,7 +55,8 @@ struct EnvParams {
 };
 
 // kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile,
-// 5 = env_kernel_sym (state phase only: any RGB output pointer is ignored)
+// 4 = env_kernel_tile_tma (tile kernel, frames through cp.async.bulk), 5 = env_kernel_sym (state phase only: any RGB
+// output pointer is ignored), 6 = env_kernel_ordered (group kernel, groups handed out in order)
 void set_kernel_choice(int choice);
 const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);

@@ -95,7 +95,8 @@ def load():
 
 
 def set_kernel_choice(choice):
-    """0 = automatic, 1 = group kernel, 2 = warp-per-env kernel, 3 = CTA-tile kernel (process-wide; identical results)."""
+    """0 = automatic, 1 = group kernel, 2 = warp-per-env kernel, 3 = CTA-tile kernel, 4 = CTA-tile kernel with TMA frame
+    stores, 5 = symbolic-only kernel, 6 = group kernel with in-order hand-out (process-wide; identical results)."""
     check(load().merlin_set_kernel_choice(int(choice)))
 
 

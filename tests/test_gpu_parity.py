@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=[1, 2, 3], ids=["group_kernel", "warp_kernel", "tile_kernel"])
 def kernel_choice(request):
-    """Every parity test runs against all three step kernels (warp owns a group / warp per env / CTA tile)."""
+    """Every parity test runs against all three step kernels (warp owns a group / warp per env / CTA tile); the two
+    measured-and-not-adopted mappings (TMA frame stores, ordered groups) have tests/test_gpu_variants.py."""
     from merlin_b200 import set_kernel_choice
     set_kernel_choice(request.param)
     yield request.param

@@ -1,0 +1,56 @@
+"""Parity of the two selectable step-kernel mappings that were measured and not adopted as defaults: the CTA-tile kernel
+with the frame phase routed through the TMA unit (choice 4: frames assembled in shared memory, one 9408-byte
+cp.async.bulk per frame) and the group kernel with groups handed out in order (choice 6).  Same bar as every other
+mapping: bit-exact observations, rewards, flags, poses and grids against the oracle and the reference fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import helpers  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[4, 6], ids=["tile_tma_kernel", "ordered_kernel"])
+def kernel_choice(request):
+    from merlin_b200 import set_kernel_choice
+    set_kernel_choice(request.param)
+    yield request.param
+    set_kernel_choice(0)
+
+
+def _parity():
+    import test_gpu_parity as tp
+    return tp
+
+
+@pytest.mark.parametrize("name", helpers.trace_names())
+def test_reference_traces(name):
+    tp = _parity()
+    helpers.replay_trace_autoreset(tp._make_gpu_env, helpers.load(f"trace_{name}.npz"))
+    helpers.replay_trace_manual_reset(tp._make_gpu_env, helpers.load(f"trace_{name}.npz"))
+
+
+@pytest.mark.parametrize("N", [1, 31, 1000, 40000])
+def test_random_rollouts_vs_oracle(N):
+    tp = _parity()
+    _, codes, _, layouts, _ = tp._mods()
+    cells, agent = layouts.generate("mediumhard", 16, range(500, 564))
+    enc = codes.unpack_to_encoding(cells, 16, 16)
+    tp._compare_batched(N, enc, agent, 60 if N < 2000 else 12, max_steps=25, seed=N)
+    tp._compare_batched(N, enc, agent, 30 if N < 2000 else 8, max_steps=25, seed=N + 1, stuck_penalty=True,
+                        exploration_bonus=0.01)
+
+
+def test_seven_actions_objects_and_guard_bands():
+    tp = _parity()
+    rng = np.random.default_rng(3)
+    enc, agent = tp._object_layouts(rng, 96, 11)
+    _, _, n_done = tp._compare_batched(3000, enc, agent, 40, n_actions=7, max_steps=23, seed=9)
+    assert n_done > 0
+    tp.test_outputs_stay_inside_their_buffers(257)
+    tp.test_outputs_stay_inside_their_buffers(9473)
+    tp.test_masked_reset_only_touches_selected_envs()
