@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "env_logic.cuh"
+#include "obs_swar.cuh"
 
 using namespace merlin;
 
@@ -57,6 +58,35 @@ int hm_step(int N, int W, int H, int max_steps, int cell_stride, int n_actions, 
         uint8_t* sym = obs_sym + (size_t)e * kSymBytes + c * 3;
         sym[0] = t; sym[1] = col; sym[2] = stt;
       }
+    uint8_t* frame = obs_rgb + (size_t)e * kImgBytes;
+    for (int c = 0; c < kChunks; ++c) {
+      const uint32_t q = chunk_lut(c);
+      const uint32_t k0 = kind[q & 0xff], k1 = kind[(q >> 16) & 0xff];
+      memcpy(frame + c * 16, atlas + k0 * kTileBytes + ((q >> 8) & 0xff) * 8, 8);
+      memcpy(frame + c * 16 + 8, atlas + k1 * kTileBytes + (q >> 24) * 8, 8);
+    }
+  }
+  return 0;
+}
+
+// The row-parallel observation (obs_swar.cuh) for N envs: symbolic image u8[N][147] and tile kinds u8[N][49], to be
+// compared with what hm_step produced by the per-cell form.  W >= 7; `cells` needs 8 bytes of slack after the last grid.
+int hm_observe_swar(int N, int W, int H, int cell_stride, const int32_t* state, const uint8_t* cells,
+                    const uint8_t* atlas, uint8_t* obs_rgb, uint8_t* obs_sym) {
+  for (int e = 0; e < N; ++e) {
+    EnvState s{};
+    const int32_t* st = state + 4 * e;
+    unpack_state(st[0], st[1], st[2], st[3], s);
+    uint64_t g[kView], seen[kView];
+    observe_swar(s, cells + (size_t)e * cell_stride, W, H, g, seen);
+    for (int vi = 0; vi < kView; ++vi) {
+      uint32_t w[6];
+      encode_group(g[vi], w);
+      memcpy(obs_sym + (size_t)e * kSymBytes + vi * 21, w, 21);
+    }
+    uint32_t kw[13];
+    kind_words(g, s.carry, kw);
+    const uint8_t* kind = reinterpret_cast<const uint8_t*>(kw);
     uint8_t* frame = obs_rgb + (size_t)e * kImgBytes;
     for (int c = 0; c < kChunks; ++c) {
       const uint32_t q = chunk_lut(c);

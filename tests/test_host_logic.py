@@ -75,8 +75,9 @@ def test_atlas_matches_literal_renderer():
 def _host_model():
     src = os.path.join(ROOT, "tests", "csrc", "host_model.cpp")
     hdr = os.path.join(ROOT, "ppo-2dgrid_b200", "csrc", "env_logic.cuh")
+    hdr2 = os.path.join(ROOT, "ppo-2dgrid_b200", "csrc", "obs_swar.cuh")
     out = os.path.join(ROOT, "tests", "csrc", "_build", "libhost_model.so")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in (src, hdr, hdr2)):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                                "-I" + os.path.dirname(hdr), src, "-o", out])
@@ -116,6 +117,13 @@ class HostModelEnv:
                          3, ctypes.c_double(-0.1), int(self.bonus != 0), ctypes.c_double(self.bonus), self.vw,
                          p(self.state), p(self.cells), p(self.visited), p(actions), p(self.atlas), p(rgb), p(sym),
                          p(rew), p(te), p(tr), p(sk))
+        # the row-parallel observation (obs_swar.cuh) must agree with the per-cell form on every call
+        if self.W >= 7:
+            rgb2, sym2 = np.zeros_like(rgb), np.zeros_like(sym)
+            padded = np.concatenate([self.cells.reshape(-1), np.zeros(8, np.uint8)])
+            self.lib.hm_observe_swar(N, self.W, self.H, self.stride, p(self.state), p(padded), p(self.atlas), p(rgb2), p(sym2))
+            assert np.array_equal(sym2, sym), "obs_swar symbolic image differs from the per-cell form"
+            assert np.array_equal(rgb2, rgb), "obs_swar tile kinds differ from the per-cell form"
         return rgb, sym, rew, te.astype(bool), tr.astype(bool), sk.astype(bool)
 
 
@@ -170,6 +178,28 @@ def test_kernel_logic_on_host_matches_oracle(n_actions, stuck, bonus, size):
         pose = hm.state[:, 0]
         assert np.array_equal(pose & 0xFF, ref.ax) and np.array_equal((pose >> 8) & 0xFF, ref.ay)
         assert np.array_equal((pose >> 16) & 3, ref.adir) and np.array_equal(hm.state[:, 1], ref.stepc)
+
+
+@pytest.mark.parametrize("W,H", [(7, 7), (7, 30), (8, 9), (9, 8), (13, 11), (16, 16), (17, 23), (31, 7), (40, 33), (255, 9)])
+def test_row_parallel_observation_equals_per_cell_form(W, H):
+    """obs_swar.cuh against gather_view + visibility + sym_of_code on grids WITHOUT a border wall: agents on every edge
+    and corner (windows hanging out of the grid on any side), every heading, every object type, carried objects."""
+    rng = np.random.default_rng(W * 1000 + H)
+    L = 400
+    objs = [(1, 0, 0)] * 6 + [(2, 5, 0)] * 4 + [(8, 1, 0), (9, 0, 0), (3, 2, 0), (4, 4, 0), (4, 4, 1), (4, 4, 2), (5, 4, 0),
+                                             (6, 0, 0), (7, 3, 0), (4, 2, 1), (5, 2, 0), (4, 0, 2), (6, 5, 0)]
+    pick = rng.integers(0, len(objs), (L, W, H))
+    enc = np.asarray(objs, np.uint8)[pick]
+    agent = np.stack([rng.integers(0, W, L), rng.integers(0, H, L), rng.integers(0, 4, L)], axis=1).astype(np.int32)
+    edge = rng.random(L) < 0.5  # half of the agents sit on an edge or in a corner
+    agent[edge, 0] = np.where(rng.random(edge.sum()) < 0.5, rng.choice([0, W - 1], edge.sum()), agent[edge, 0])
+    agent[edge, 1] = np.where(rng.random(edge.sum()) < 0.5, rng.choice([0, H - 1], edge.sum()), agent[edge, 1])
+    hm = HostModelEnv(codes.pack_encoding(enc), agent, W, H, 100, n_actions=7)
+    carried = np.asarray([0, 0, codes.pack(5, 4, 0), codes.pack(6, 0, 0), codes.pack(7, 3, 0)], np.int32)[rng.integers(0, 5, L)]
+    hm.state[:, 0] |= carried << 24
+    rgb, sym, *_ = hm.call(np.zeros(L, np.int64), do_step=False)  # asserts the two forms agree
+    assert (sym[:, 3, 6, 0] != 0).all()  # the agent's own cell is always visible
+    assert len(np.unique(sym[..., 0])) >= 9
 
 
 def test_visibility_bitmask_exhaustive_rows():
