@@ -164,6 +164,11 @@ int64_t merlin_env_launch_count(merlin_env_t* h);             /* kernels launche
  * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out.
  * All kernels produce identical results for the outputs they write; "automatic" never picks 4 or 6 (measured slower). */
 int merlin_set_kernel_choice(int choice);
+/* Tuning/testing knob, process-wide: how gen_obs is computed.  0 = automatic (default): the symbolic-only kernel works
+ * on seven window cells per 64-bit register (csrc/obs_swar.cuh; grids at least 7 wide), the frame kernels cell by cell
+ * (csrc/env_logic.cuh) -- the faster choice for each, measured;  1 = cell by cell everywhere;  2 = the row-parallel form
+ * in every kernel that has it (symbolic-only, tile, ordered).  Identical results. */
+int merlin_set_observation_path(int path);
 /* Name of the kernel merlin_env_step launches for this handle (rgb != 0: with an RGB observation). */
 const char* merlin_env_step_kernel(merlin_env_t* h, int rgb);
 

@@ -459,6 +459,13 @@ int merlin_set_kernel_choice(int choice) {
   return MERLIN_OK;
 }
 
+int merlin_set_observation_path(int path) {
+  if (path < 0 || path > 2)
+    return fail(MERLIN_EINVAL, "observation path must be 0 (automatic), 1 (per-cell form) or 2 (row-parallel form wherever built)");
+  set_observation_path(path);
+  return MERLIN_OK;
+}
+
 int merlin_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv, float* ret,
                int32_t T, int32_t N, double gamma, double lam, void* stream) {
   if (!rew || !val || !done || !last_val || !adv || !ret) return fail(MERLIN_EINVAL, "merlin_gae: null pointer");

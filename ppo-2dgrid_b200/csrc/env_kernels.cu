@@ -25,6 +25,7 @@
 
 #include "env_kernels.cuh"
 #include "env_logic.cuh"
+#include "obs_swar.cuh"
 
 namespace merlin {
 
@@ -102,9 +103,53 @@ __device__ __forceinline__ void emit_sym_rows(uint8_t* out, const uint8_t* sym_s
   }
 }
 
+// One env's 147-byte symbolic image from its seven visible-code groups (obs_swar.cuh) into shared memory at `row`
+// (any alignment: rows of consecutive lanes are 147 bytes apart).  The image is assembled as 37 little-endian words in
+// registers, funnel-shifted by this lane's misalignment and stored as 35 aligned words; the words that straddle the
+// row's two ends are shared with the neighbouring lanes' rows and go out as single bytes.
+__device__ __forceinline__ void store_sym_row(uint8_t* row, const uint64_t (&g)[kView]) {
+  uint32_t r[38];
+  {
+    uint64_t acc = 0;
+    int have = 0, n = 0;  // compile-time after unrolling: every shift below is an immediate
+#pragma unroll
+    for (int vi = 0; vi < kView; ++vi) {
+      uint32_t w[6];
+      encode_group(g[vi], w);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        acc |= (uint64_t)w[i] << (8 * have);
+        have += i < 5 ? 4 : 1;
+        if (have >= 4) { r[n++] = (uint32_t)acc; acc >>= 32; have -= 4; }
+      }
+    }
+    r[n++] = (uint32_t)acc;  // bytes 144..146 (+ one zero)
+    r[n] = 0;                // n == 37
+  }
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(row);
+  const uint32_t s = addr & 3u, sh = 8u * s;
+  uint8_t* base = row - s;  // word-aligned
+  uint32_t prev = 0;
+#pragma unroll
+  for (int k = 0; k < 38; ++k) {
+    const uint32_t word = __funnelshift_l(prev, r[k], sh);  // bytes 4k - s .. 4k - s + 3 of the image
+    prev = r[k];
+    if (k >= 1 && k <= 35) {
+      *reinterpret_cast<uint32_t*>(base + 4 * k) = word;
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * k + b - (int)s;  // image byte held by byte b of this word
+        if (i >= 0 && i < kSymBytes) base[4 * k + b] = (uint8_t)(word >> (8 * b));
+      }
+    }
+  }
+}
+
 // State phase, one env per lane, for the G envs e0 .. e0+G-1 (lanes >= G idle).  Must be called by a full warp.
 // Leaves kinds_s[lane][kKindStride] / sym_s[lane][147] filled for the envs whose bit is set in the returned mask.
-template <int G, bool STEP>
+// SWAR = true: the observation is computed on window rows (obs_swar.cuh; needs W >= 7), else cell by cell.
+template <int G, bool STEP, bool SWAR = false>
 __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags& f, int e0, int lane, uint8_t* kinds_s,
                                                 uint8_t* sym_s) {
   const int e = e0 + lane;
@@ -205,23 +250,36 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
     const uint8_t* grid = f.mutable_grid ? p.cells + (size_t)e * p.cell_stride
                                          : p.pool_cells + (size_t)s.layout * p.cell_stride;
     uint8_t* kind = kinds_s + lane * kKindStride;
-    const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
-    const uint64_t vis = visibility(transp);
-    uint8_t* sym = sym_s + lane * kSymBytes;
+    if (SWAR) {
+      uint64_t g[kView], seen[kView];
+      observe_swar(s, grid, p.W, p.H, g, seen);
+      if (f.want_rgb) {
+        uint32_t kw[13];
+        kind_words(g, s.carry, kw);
+        uint32_t* kdst = reinterpret_cast<uint32_t*>(kind);  // kKindStride = 52: word-aligned rows
 #pragma unroll
-    for (int vi = 0; vi < kView; ++vi) {
+        for (int i = 0; i < 13; ++i) kdst[i] = kw[i];
+      }
+      if (f.want_sym) store_sym_row(sym_s + lane * kSymBytes, g);
+    } else {
+      const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
+      const uint64_t vis = visibility(transp);
+      uint8_t* sym = sym_s + lane * kSymBytes;
 #pragma unroll
-      for (int vj = 0; vj < kView; ++vj) {
-        const int c = vi * kView + vj;
-        const bool seen = (vis >> (vj * kView + vi)) & 1;
-        uint32_t code = kind[c];
-        const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
-        if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
-        kind[c] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
-        if (f.want_sym) {
-          uint8_t t = 0, col = 0, stt = 0;
-          if (seen) sym_of_code(code, t, col, stt);
-          sym[c * 3 + 0] = t; sym[c * 3 + 1] = col; sym[c * 3 + 2] = stt;
+      for (int vi = 0; vi < kView; ++vi) {
+#pragma unroll
+        for (int vj = 0; vj < kView; ++vj) {
+          const int c = vi * kView + vj;
+          const bool seen = (vis >> (vj * kView + vi)) & 1;
+          uint32_t code = kind[c];
+          const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
+          if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
+          kind[c] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
+          if (f.want_sym) {
+            uint8_t t = 0, col = 0, stt = 0;
+            if (seen) sym_of_code(code, t, col, stt);
+            sym[c * 3 + 0] = t; sym[c * 3 + 1] = col; sym[c * 3 + 2] = stt;
+          }
         }
       }
     }
@@ -279,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 //   G=8, 256 x 2  1.034    G=16, 256 x 2  1.024    G=16, 128 x 4  1.021    G=4, 128 x 4  0.920
 // i.e. in-order hand-out lifts the group mapping from 0.92 (static assignment) to 1.05, but more concurrent state phases
 // buy nothing over the tile kernel: its limit is the store stream, not the state-phase chain.  Kept selectable (choice 6).
-template <int G, bool STEP, int THREADS, int MINB>
+template <int G, bool STEP, int THREADS, int MINB, bool SWAR = false>
 __global__ void __launch_bounds__(THREADS, MINB) env_kernel_ordered(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -304,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_ordered(const EnvPar
     int next = 0;
     if (lane == 0) next = (int)atomicAdd(&p.sched[0], 1u);
     const int e0 = g * G;
-    const unsigned render_mask = state_phase<G, STEP>(p, f, e0, lane, kinds_s, sym_s);
+    const unsigned render_mask = state_phase<G, STEP, SWAR>(p, f, e0, lane, kinds_s, sym_s);
     if (f.want_sym && render_mask)
       emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(G, p.N - e0), render_mask, lane, 32);
     if (f.want_rgb) {
@@ -345,7 +403,7 @@ __host__ __device__ constexpr int tile_smem_bytes(int T) {
   return kAtlasBytes + ((T * kKindStride + T * kSymBytes + 15) & ~15) + 16;
 }
 
-template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
+template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm, bool SWAR = false>
 __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams p, const int n_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -375,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams
   while (tile < n_tiles) {
     const int e0 = tile * T;
     if (warp == 0) {
-      const unsigned m = state_phase<T, STEP>(p, f, e0, lane, kinds_s, sym_s);
+      const unsigned m = state_phase<T, STEP, SWAR>(p, f, e0, lane, kinds_s, sym_s);
       if (lane == 0) *mask_s = m;
     } else if (threadIdx.x == 32) {
       s_next = (int)atomicAdd(&p.sched[0], 1u);
@@ -509,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile_tma(const EnvPa
 // blit map and the frame loop the state phase fits in ~72 registers, so six to seven 128-thread CTAs are resident per
 // SM instead of one 256-thread CTA of env_kernel<32>: this mode is instruction/latency-bound (449 B per env-step), and
 // occupancy is what it needs.
-template <bool STEP>
+template <bool STEP, bool SWAR = false>
 __global__ void __launch_bounds__(128) env_kernel_sym(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -521,9 +579,24 @@ __global__ void __launch_bounds__(128) env_kernel_sym(const EnvParams p, const i
   const int g = blockIdx.x * (blockDim.x >> 5) + warp;
   if (g >= n_groups) return;
   const int e0 = g * 32;
-  const unsigned render_mask = state_phase<32, STEP>(p, f, e0, lane, kinds_s, sym_s);
+  const unsigned render_mask = state_phase<32, STEP, SWAR>(p, f, e0, lane, kinds_s, sym_s);
   if (f.want_sym && render_mask)
     emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(32, p.N - e0), render_mask, lane, 32);
+}
+
+// Observation path.  Measured on B200 at 1M envs: the row-parallel form (obs_swar.cuh, 30 % fewer instructions, 56
+// instead of 72 registers) lifts the symbolic-only kernel from 7.1e9 to 1.07e10 env-steps/s (0.49 -> 0.73 of the HBM
+// roofline of its 449 B/step): that kernel is instruction-bound and runs 32 warps per SM.  The tile kernel gets SLOWER
+// with it (1.08 -> 1.01 of the copy peak): there ONE warp per CTA runs the state phase while three wait, so what
+// counts is that warp's latency, and the per-cell form's 49 independent loads / cells have more instruction-level
+// parallelism than the dependent 64-bit shift / multiply chains of the row form.  The ordered-group kernel is
+// indifferent (1.05 either way).  Hence: 0 = automatic = row-parallel in the symbolic-only kernel only,
+// 1 = per-cell everywhere, 2 = row-parallel in every kernel that has it (symbolic-only, tile, ordered; tests, A/B).
+static int g_observation_path = 0;
+void set_observation_path(int path) { g_observation_path = path; }
+static bool use_swar(const EnvParams& p, bool frame_kernel) {
+  if (p.W < kView || g_observation_path == 1) return false;
+  return g_observation_path == 2 || !frame_kernel;
 }
 
 template <bool STEP>
@@ -531,7 +604,9 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, cudaStream_t stream) {
   constexpr int threads = 128, warps = threads / 32;
   const int n_groups = (p.N + 31) / 32;
   const size_t smem = warps * warp_smem_bytes(32);
-  env_kernel_sym<STEP><<<(n_groups + warps - 1) / warps, threads, smem, stream>>>(p, n_groups);
+  const int grid = (n_groups + warps - 1) / warps;
+  if (use_swar(p, false)) env_kernel_sym<STEP, true><<<grid, threads, smem, stream>>>(p, n_groups);
+  else env_kernel_sym<STEP, false><<<grid, threads, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
 }
 
@@ -969,20 +1044,25 @@ static cudaError_t launch_group_kernel(const EnvParams& p, int sm_count, cudaStr
   return cudaGetLastError();
 }
 
-template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
-static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+template <int T, bool STEP, bool SWAR, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
+static cudaError_t launch_tile_kernel_impl(const EnvParams& p, int sm_count, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_smem_bytes(T);
   static int blocks_per_sm_dev[64] = {};
   int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
   if (!blocks_per_sm) {
-    cudaError_t err = resident_ctas(env_kernel_tile<T, STEP, THREADS, MINB>, THREADS, smem, blocks_per_sm);
+    cudaError_t err = resident_ctas(env_kernel_tile<T, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
     if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
   const int grid = min(sm_count * blocks_per_sm, n_tiles);
-  env_kernel_tile<T, STEP, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p, n_tiles);
+  env_kernel_tile<T, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_tiles);
   return cudaGetLastError();
+}
+template <int T, bool STEP>
+static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  return use_swar(p, true) ? launch_tile_kernel_impl<T, STEP, true>(p, sm_count, stream)
+                     : launch_tile_kernel_impl<T, STEP, false>(p, sm_count, stream);
 }
 
 #ifndef MERLIN_ORD_G
@@ -990,21 +1070,26 @@ static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStre
 #define MERLIN_ORD_THREADS 128
 #define MERLIN_ORD_CTAS 3
 #endif
-template <int G, bool STEP, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
-static cudaError_t launch_ordered_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+template <int G, bool STEP, bool SWAR, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
+static cudaError_t launch_ordered_kernel_impl(const EnvParams& p, int sm_count, cudaStream_t stream) {
   constexpr int warps = THREADS / 32;
   const int n_groups = (p.N + G - 1) / G;
   const size_t smem = kAtlasBytes + warps * warp_smem_bytes(G);
   static int blocks_per_sm_dev[64] = {};
   int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
   if (!blocks_per_sm) {
-    cudaError_t err = resident_ctas(env_kernel_ordered<G, STEP, THREADS, MINB>, THREADS, smem, blocks_per_sm);
+    cudaError_t err = resident_ctas(env_kernel_ordered<G, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
     if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
   const int grid = min(sm_count * blocks_per_sm, (n_groups + warps - 1) / warps);
-  env_kernel_ordered<G, STEP, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p, n_groups);
+  env_kernel_ordered<G, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
+}
+template <int G, bool STEP>
+static cudaError_t launch_ordered_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+  return use_swar(p, true) ? launch_ordered_kernel_impl<G, STEP, true>(p, sm_count, stream)
+                     : launch_ordered_kernel_impl<G, STEP, false>(p, sm_count, stream);
 }
 
 #ifndef MERLIN_TMA_T

@@ -58,6 +58,9 @@ struct EnvParams {
 // 4 = env_kernel_tile_tma (tile kernel, frames through cp.async.bulk), 5 = env_kernel_sym (state phase only: any RGB
 // output pointer is ignored), 6 = env_kernel_ordered (group kernel, groups handed out in order)
 void set_kernel_choice(int choice);
+// observation path: 0 = automatic (row-parallel obs_swar.cuh in the symbolic-only kernel when W >= 7), 1 = per-cell
+// everywhere, 2 = row-parallel in every kernel that has it (symbolic-only, tile, ordered)
+void set_observation_path(int path);
 const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
 cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream);

@@ -7,6 +7,6 @@ Importing this package does not need a GPU; creating an env or calling `gae` doe
 from . import codes, layouts, tiles  # noqa: F401
 from .env import BatchedMerlinEnv, OBS_SHAPE, SYM_SHAPE  # noqa: F401
 from .gae import gae  # noqa: F401
-from ._lib import set_kernel_choice  # noqa: F401
+from ._lib import set_kernel_choice, set_observation_path  # noqa: F401
 
 __all__ = ["BatchedMerlinEnv", "gae", "codes", "layouts", "tiles", "OBS_SHAPE", "SYM_SHAPE"]

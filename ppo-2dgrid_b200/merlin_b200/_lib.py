@@ -20,7 +20,7 @@ EXPORTS = (
     "merlin_env_generate_layouts", "merlin_env_read_layouts", "merlin_env_layout_count",
     "merlin_env_set_tile_atlas", "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step",
     "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
-    "merlin_set_kernel_choice", "merlin_env_step_kernel", "merlin_env_render", "merlin_env_render_f32", "merlin_env_full_obs", "merlin_gae",
+    "merlin_set_kernel_choice", "merlin_set_observation_path", "merlin_env_step_kernel", "merlin_env_render", "merlin_env_render_f32", "merlin_env_full_obs", "merlin_gae",
     "merlin_pack_cell", "merlin_last_error", "merlin_version",
 )
 
@@ -70,6 +70,8 @@ def load():
     lib.merlin_env_launch_count.restype = i64
     lib.merlin_set_kernel_choice.argtypes = [C.c_int]
     lib.merlin_set_kernel_choice.restype = C.c_int
+    lib.merlin_set_observation_path.argtypes = [C.c_int]
+    lib.merlin_set_observation_path.restype = C.c_int
     lib.merlin_env_full_obs.argtypes = [vp, vp, vp]
     lib.merlin_env_full_obs.restype = C.c_int
     lib.merlin_env_render.argtypes = [vp, vp, i64, vp, i32, vp, i32, vp]
@@ -89,6 +91,8 @@ def load():
                  "merlin_env_read_state", "merlin_env_bad_actions", "merlin_gae"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
+    if os.environ.get("MERLIN_OBSERVATION_PATH"):
+        check(lib.merlin_set_observation_path(int(os.environ["MERLIN_OBSERVATION_PATH"])))
     if os.environ.get("MERLIN_KERNEL_CHOICE"):
         check(lib.merlin_set_kernel_choice(int(os.environ["MERLIN_KERNEL_CHOICE"])))
     return lib
@@ -98,6 +102,12 @@ def set_kernel_choice(choice):
     """0 = automatic, 1 = group kernel, 2 = warp-per-env kernel, 3 = CTA-tile kernel, 4 = CTA-tile kernel with TMA frame
     stores, 5 = symbolic-only kernel, 6 = group kernel with in-order hand-out (process-wide; identical results)."""
     check(load().merlin_set_kernel_choice(int(choice)))
+
+
+def set_observation_path(path):
+    """0 = automatic (row-parallel gen_obs in the symbolic-only kernel), 1 = per-cell everywhere, 2 = row-parallel in
+    every kernel that has it (symbolic-only, tile, ordered).  Process-wide; identical results."""
+    check(load().merlin_set_observation_path(int(path)))
 
 
 def check(rc):

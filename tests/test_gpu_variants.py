@@ -14,12 +14,17 @@ import helpers  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[4, 6], ids=["tile_tma_kernel", "ordered_kernel"])
+@pytest.fixture(autouse=True, params=[(4, 0), (6, 0), (3, 2), (6, 2)],
+                ids=["tile_tma_kernel", "ordered_kernel", "tile_kernel_row_obs", "ordered_kernel_row_obs"])
 def kernel_choice(request):
-    from merlin_b200 import set_kernel_choice
-    set_kernel_choice(request.param)
+    """(kernel choice, observation path): path 2 = the row-parallel gen_obs (obs_swar.cuh) in kernels that default to the
+    per-cell form (the symbolic-only kernel uses it by default and is covered by the main suites)."""
+    from merlin_b200 import set_kernel_choice, set_observation_path
+    set_kernel_choice(request.param[0])
+    set_observation_path(request.param[1])
     yield request.param
     set_kernel_choice(0)
+    set_observation_path(0)
 
 
 def _parity():
@@ -43,6 +48,30 @@ def test_random_rollouts_vs_oracle(N):
     tp._compare_batched(N, enc, agent, 60 if N < 2000 else 12, max_steps=25, seed=N)
     tp._compare_batched(N, enc, agent, 30 if N < 2000 else 8, max_steps=25, seed=N + 1, stuck_penalty=True,
                         exploration_bonus=0.01)
+
+
+def test_symbolic_only_kernel_per_cell_and_row_forms_agree():
+    """The symbolic-only kernel under observation path 1 (per-cell) and 0 / 2 (row-parallel): same images, bit for bit,
+    on grids with every object type, ragged batch sizes and a grid narrower than the window (always per-cell)."""
+    import torch
+    from merlin_b200 import set_kernel_choice, set_observation_path
+    tp = _parity()
+    rng = np.random.default_rng(17)
+    for size, N in ((11, 4099), (16, 33), (6, 500)):
+        enc, agent = tp._object_layouts(rng, 64, size)
+        outs = []
+        for path in (1, 0):
+            set_kernel_choice(0)
+            set_observation_path(path)
+            env = tp._make_gpu_env(N, enc, agent, n_actions=7, max_steps=19, want_rgb=False)
+            r2 = np.random.default_rng(5)
+            _, sym = env.reset()
+            frames = [sym.clone()]
+            for _ in range(25):
+                _, _, _, _, info = env.step(torch.as_tensor(r2.integers(0, 7, N), device="cuda:0"))
+                frames.append(info["obs_symbolic"].clone())
+            outs.append(torch.stack(frames))
+        assert torch.equal(outs[0], outs[1]), size
 
 
 def test_seven_actions_objects_and_guard_bands():
