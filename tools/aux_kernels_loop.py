@@ -26,3 +26,15 @@ for _ in range(3):
 env.generate_layouts("mediumhard", 2, 65536)
 torch.cuda.synchronize()
 print("done")
+# float32 minibatch frames (render_f32_kernel) and the symbolic-only step kernel on the row-parallel gen_obs
+out = torch.empty((N, 14, 14, 48), dtype=torch.float32, device=dev)
+for _ in range(3):
+    env.render(sym, idx, out=out, blocked=True, dtype=torch.float32)
+del out
+env2 = BatchedMerlinEnv(1 << 20, width=16, height=16, device=dev, generate=("mediumhard", 3, 8192), want_rgb=False)
+env2.reset()
+a2 = torch.randint(0, 3, (4, 1 << 20), device=dev)
+for i in range(6):
+    env2.step(a2[i % 4])
+torch.cuda.synchronize()
+print("done 2")
