@@ -567,15 +567,24 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile_tma(const EnvPa
 // blit map and the frame loop the state phase fits in ~72 registers, so six to seven 128-thread CTAs are resident per
 // SM instead of one 256-thread CTA of env_kernel<32>: this mode is instruction/latency-bound (449 B per env-step), and
 // occupancy is what it needs.
+__host__ __device__ constexpr int sym_kernel_warp_smem(bool swar) {
+  return swar ? 32 * kSymBytes : warp_smem_bytes(32);
+}
+
+#ifndef MERLIN_SYM_MINB
+#define MERLIN_SYM_MINB 10  // 48 registers, 40 warps/SM: 1.16e10 env-steps/s at 1M envs (unconstrained, 56 registers: 1.11e10; 12 CTAs, 40 registers + spills: 1.04e10)
+#endif
 template <bool STEP, bool SWAR = false>
-__global__ void __launch_bounds__(128) env_kernel_sym(const EnvParams p, const int n_groups) {
+__global__ void __launch_bounds__(128, SWAR ? MERLIN_SYM_MINB : 1) env_kernel_sym(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const Flags f(p);
-  uint8_t* warp_s = smem + warp * warp_smem_bytes(32);
-  uint8_t* kinds_s = warp_s;
-  uint8_t* sym_s = warp_s + 32 * kKindStride;
+  Flags f(p);
+  f.want_rgb = false;  // no frame phase here: tile kinds are not produced either
+  // the row-parallel form keeps the window in registers; only the per-cell form stages the 49 codes per env
+  uint8_t* warp_s = smem + warp * sym_kernel_warp_smem(SWAR);
+  uint8_t* kinds_s = SWAR ? nullptr : warp_s;
+  uint8_t* sym_s = SWAR ? warp_s : warp_s + 32 * kKindStride;
   const int g = blockIdx.x * (blockDim.x >> 5) + warp;
   if (g >= n_groups) return;
   const int e0 = g * 32;
@@ -603,10 +612,11 @@ template <bool STEP>
 static cudaError_t launch_sym_kernel(const EnvParams& p, cudaStream_t stream) {
   constexpr int threads = 128, warps = threads / 32;
   const int n_groups = (p.N + 31) / 32;
-  const size_t smem = warps * warp_smem_bytes(32);
   const int grid = (n_groups + warps - 1) / warps;
-  if (use_swar(p, false)) env_kernel_sym<STEP, true><<<grid, threads, smem, stream>>>(p, n_groups);
-  else env_kernel_sym<STEP, false><<<grid, threads, smem, stream>>>(p, n_groups);
+  if (use_swar(p, false))
+    env_kernel_sym<STEP, true><<<grid, threads, warps * sym_kernel_warp_smem(true), stream>>>(p, n_groups);
+  else
+    env_kernel_sym<STEP, false><<<grid, threads, warps * sym_kernel_warp_smem(false), stream>>>(p, n_groups);
   return cudaGetLastError();
 }
 
