@@ -182,9 +182,10 @@ class BatchedMerlinEnv:
             return raw(self.device.index)
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, mask=None, out_obs=None, out_symbolic=None):
-        """(Re)start all envs (mask=None) or those with mask[e] != 0.  Returns (obs_rgb, obs_symbolic)."""
-        obs = out_obs if out_obs is not None else self.obs
+    def reset(self, mask=None, out_obs=None, out_symbolic=None, frames=True):
+        """(Re)start all envs (mask=None) or those with mask[e] != 0.  Returns (obs_rgb, obs_symbolic).
+        `frames=False`: no RGB frames for this call (the symbolic-only kernel runs; obs_rgb is None)."""
+        obs = (out_obs if out_obs is not None else self.obs) if frames else None
         sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
         mptr = None
         if mask is not None:
@@ -194,17 +195,19 @@ class BatchedMerlinEnv:
                                               sym.data_ptr() if sym is not None else None, self._stream()))
         return obs, sym
 
-    def step(self, actions, out_obs=None, out_symbolic=None, out=None):
+    def step(self, actions, out_obs=None, out_symbolic=None, out=None, frames=True):
         """actions: int64 CUDA tensor [N] (numpy/int lists are copied over).  Returns the gymnasium 5-tuple
         (obs u8[N,56,56,3], reward f32[N], terminated bool[N], truncated bool[N], info) with device tensors that
-        are REUSED by the next call unless `out_obs` / `out_symbolic` point into caller storage (e.g. a rollout slot)."""
+        are REUSED by the next call unless `out_obs` / `out_symbolic` point into caller storage (e.g. a rollout slot).
+        `frames=False`: this call writes no RGB frames (obs is None; the symbolic-only kernel runs) -- for callers that
+        expand the symbolic image themselves (`render(..., dtype=torch.float32)` straight into the policy's input)."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
         if actions.device != self.device or actions.dtype != torch.int64 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.int64).contiguous()
         if actions.numel() != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
-        obs = out_obs if out_obs is not None else self.obs
+        obs = (out_obs if out_obs is not None else self.obs) if frames else None
         sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
         b = out if out is not None else self
         _lib.check(self._lib.merlin_env_step(

@@ -48,13 +48,18 @@ class CNNFeatureExtractor(nn.Module):
         """x: `[N, C, H, W]` float pixel values in 0..255 (the reference's input convention)."""
         return self.network(x / 255.0)
 
-    def forward_blocked(self, xb):
+    def blocked_weight(self):
+        """conv1's `[32, 3, 8, 8]` stride-4 kernel re-indexed as the `[32, 48, 2, 2]` stride-1 kernel over
+        `space_to_depth4` input, 1/255 folded in.  A rollout can form it once (`CNNActorCritic.blocked_weights`)."""
+        return _space_to_depth4_weight(self.network[0].weight) * (1.0 / 255.0)
+
+    def forward_blocked(self, xb, weight=None):
         """Same function on `space_to_depth4` input (float pixel values 0..255).  The first layer (8x8, stride 4, 3
         input channels) is evaluated as a 2x2 stride-1 convolution over 48 channels with the SAME parameters
         (re-indexed on the fly, 1/255 folded into them): identical sums in a different order, and a shape cuDNN runs
         several times faster than C = 3."""
-        conv1 = self.network[0]
-        h = torch.nn.functional.conv2d(xb, _space_to_depth4_weight(conv1.weight) * (1.0 / 255.0), conv1.bias)
+        w = self.blocked_weight() if weight is None else weight
+        h = torch.nn.functional.conv2d(xb, w, self.network[0].bias)
         return self.network[1:](h)
 
 
@@ -71,8 +76,8 @@ class _ActorCriticBase(nn.Module):
         """(logits `[B, A]`, value `[B]`) -- the functional entry point used for stacked per-task weights."""
         return self._logits_value(obs)
 
-    def act(self, obs, deterministic=False):
-        logits, value = self._logits_value(obs)
+    def act(self, obs, deterministic=False, **kw):
+        logits, value = self._logits_value(obs, **kw)
         logp_all = torch.log_softmax(logits, dim=-1)
         if deterministic:
             action = torch.argmax(logits, dim=1)
@@ -103,17 +108,23 @@ class CNNActorCritic(_ActorCriticBase):
             return x.permute(0, 3, 1, 2).float()
         return x.float()
 
-    def _logits_value(self, obs):
+    def blocked_weights(self):
+        """The two trunks' re-indexed first-layer kernels, for `act(..., blocked=...)`: a rollout whose parameters do
+        not change between steps forms them once instead of at every step (four small kernels per step)."""
+        return self.actor_extractor.blocked_weight(), self.critic_extractor.blocked_weight()
+
+    def _logits_value(self, obs, blocked=None):
+        wa, wc = blocked if blocked is not None else (None, None)
         if obs.ndim == 4 and obs.shape[-1] == 48:
             # frames already in the blocked layout [N, H/4, W/4, 48] (BatchedMerlinEnv.render(..., blocked=True)), pixel
             # values 0..255 as uint8 or -- written by the render kernel itself, nothing to cast or copy here -- float32
             xb = obs.permute(0, 3, 1, 2)
             if xb.dtype != torch.float32:
                 xb = xb.float()
-            fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
+            fa, fc = self.actor_extractor.forward_blocked(xb, wa), self.critic_extractor.forward_blocked(xb, wc)
         elif self.blocked_first_layer and obs.ndim == 4 and obs.shape[-1] == 3:
             xb = space_to_depth4(obs)  # shared by both trunks
-            fa, fc = self.actor_extractor.forward_blocked(xb), self.critic_extractor.forward_blocked(xb)
+            fa, fc = self.actor_extractor.forward_blocked(xb, wa), self.critic_extractor.forward_blocked(xb, wc)
         else:
             obs = self._format_obs(obs)
             fa, fc = self.actor_extractor(obs), self.critic_extractor(obs)

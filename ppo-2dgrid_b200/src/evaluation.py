@@ -22,29 +22,41 @@ def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=Non
                    env=None, act_fn=None):
     """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)]).
     `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` replaces `policy.act` (e.g. per-task adapted weights)."""
+    from .actor_critic import CNNActorCritic
     seeds = [int(s) for s in seeds]
     B = len(seeds)
     cells, agent = _layouts.generate(difficulty, size, seeds)
+    # a CNN policy acting by itself needs no u8 frames at all: the step kernel writes the 147-byte symbolic image only and
+    # the policy's float32 first-layer input is rendered from it (two launches instead of a frame + three cast/layout passes)
+    lean = act_fn is None and isinstance(policy, CNNActorCritic) and policy.blocked_first_layer
     if env is None or env.num_envs != B:
         env = BatchedMerlinEnv(B, cells, agent, width=size, height=size, max_steps=max_steps, device=device,
-                               reset_mode="same", want_symbolic=False)
+                               reset_mode="same", want_symbolic=lean)
     else:
         env.upload_layouts(cells, agent)
+        lean = lean and env.obs_symbolic is not None
     env.set_cursors(np.arange(B, dtype=np.int32))
     dev = env.device
     ret = torch.zeros(B, dtype=torch.float32, device=dev)
     length = torch.zeros(B, dtype=torch.int32, device=dev)
     goal = torch.zeros(B, dtype=torch.bool, device=dev)
     finished = torch.zeros(B, dtype=torch.bool, device=dev)
-    obs, _ = env.reset()
+    obs, _ = env.reset(frames=not lean)
     was_training = policy.training
     policy.eval()
-    if act_fn is None:
+    if lean:
+        weights = policy.blocked_weights()
+        policy_in = torch.empty((B, 14, 14, 48), dtype=torch.float32, device=dev)
+
+        def act_fn(_):
+            x = env.render(env.obs_symbolic, out=policy_in, blocked=True, dtype=torch.float32)
+            return policy.act(x, deterministic=deterministic, blocked=weights)[0]
+    elif act_fn is None:
         def act_fn(o):
             return policy.act(o, deterministic=deterministic)[0]
     for t in range(env.max_steps):
         action = act_fn(obs)
-        obs, _, term, _, info = env.step(action)
+        obs, _, term, _, info = env.step(action, frames=not lean)
         first = (info["episode_length"] > 0) & ~finished
         ret = torch.where(first, info["episode_return"], ret)
         length = torch.where(first, info["episode_length"], length)

@@ -121,11 +121,15 @@ class FOMAML:
     def _rollout_body(self, env, policy, params, steps, buf):
         obs = buf["obs"]
         env.reset(out_obs=obs[0])
+        # shared weights do not change during the rollout: form the re-indexed first-layer kernels once, not per step
+        kw = {}
+        if params is None and self.use_cnn and getattr(policy, "blocked_first_layer", False):
+            kw["blocked"] = policy.blocked_weights()
         for t in range(steps):
-            a, lp, v = self._act(policy, params, obs[t])
+            a, lp, v = self._act(policy, params, obs[t], **kw)
             env.step(a, out_obs=obs[t + 1], out=buf["rows"][t])
             buf["act"][t].copy_(a); buf["logp"][t].copy_(lp); buf["val"][t].copy_(v)
-        buf["last_val"].copy_(self._act(policy, params, obs[steps])[2])
+        buf["last_val"].copy_(self._act(policy, params, obs[steps], **kw)[2])
 
     @staticmethod
     def _rollout_result(buf, steps):
@@ -163,10 +167,10 @@ class FOMAML:
         graph.replay()
         return self._rollout_result(buf, steps)
 
-    def _act(self, policy, params, obs):
+    def _act(self, policy, params, obs, **kw):
         """Sampled action, its log-probability and the value for one frame per task."""
         if params is None:
-            return policy.act(self._fmt(obs), deterministic=False)
+            return policy.act(self._fmt(obs), deterministic=False, **kw)
         logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
         logits, value = logits.squeeze(1), value.squeeze(1)
         logp_all = torch.log_softmax(logits, dim=-1)

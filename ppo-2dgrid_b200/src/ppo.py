@@ -78,11 +78,13 @@ class PPO:
 
         if self.batched:
             T, N = self.buffer.horizon, self.num_envs
-            self._last_obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=self.device)
             if self.obs_storage == "symbolic":
                 self._last_sym = torch.zeros((N, 7, 7, 3), dtype=torch.uint8, device=self.device)
+                self._policy_in = torch.zeros((N, 14, 14, 48), dtype=torch.float32, device=self.device)
                 self._mb_frames = torch.zeros((min(self.minibatch_size, self.batch_size), 14, 14, 48),
                                               dtype=self.minibatch_frames, device=self.device)
+            else:
+                self._last_obs = torch.zeros((N,) + self.obs_shape, dtype=torch.uint8, device=self.device)
             self._ep_ret = torch.zeros((T, N), dtype=torch.float32, device=self.device)
             self._ep_len = torch.zeros((T, N), dtype=torch.int32, device=self.device)
             self._last_value = torch.zeros(N, dtype=torch.float32, device=self.device)
@@ -114,22 +116,32 @@ class PPO:
     def _rollout_body(self):
         env, buf, T = self.env, self.buffer, self.buffer.horizon
         sym = self.obs_storage == "symbolic"
-        if sym:  # frames live in one reusable buffer (the policy's input); the rollout receives the symbolic images
-            env.reset(out_obs=self._last_obs, out_symbolic=buf.obs_slot(0))
+        # the parameters do not change during a rollout: the re-indexed first-layer kernels are formed once
+        w = self.ac.blocked_weights() if self.use_cnn and self.ac.blocked_first_layer else None
+        kw = {} if w is None else {"blocked": w}
+        if sym:
+            # symbolic storage: the step kernel writes the 147-byte images straight into the rollout and NO frames (the
+            # symbolic-only kernel runs); the policy's float32 input is rendered from the image it is about to act on
+            def policy_input(t):
+                src = buf.obs_slot(t) if t < T else self._last_sym
+                return env.render(src, out=self._policy_in, blocked=True, dtype=torch.float32)
+            env.reset(out_symbolic=buf.obs_slot(0), frames=False)
         else:
+            def policy_input(t):
+                return buf.obs_slot(t) if t < T else self._last_obs
             env.reset(out_obs=buf.obs_slot(0))
         for t in range(T):
-            action, logp, value = self.ac.act(self._last_obs if sym else buf.obs_slot(t), deterministic=False)
-            nxt = buf.obs_slot(t + 1) if t + 1 < T else (self._last_sym if sym else self._last_obs)
+            action, logp, value = self.ac.act(policy_input(t), deterministic=False, **kw)
             if sym:
-                env.step(action, out_obs=self._last_obs, out_symbolic=nxt, out=self._rows[t])
+                env.step(action, out_symbolic=buf.obs_slot(t + 1) if t + 1 < T else self._last_sym, out=self._rows[t],
+                         frames=False)
             else:
-                env.step(action, out_obs=nxt, out=self._rows[t])
+                env.step(action, out_obs=buf.obs_slot(t + 1) if t + 1 < T else self._last_obs, out=self._rows[t])
             shape = buf.actions[t].shape  # [N], or [] for a single batched env (the reference's [T] buffers)
             buf.actions[t].copy_(action.reshape(shape))
             buf.logprobs[t].copy_(logp.reshape(shape))
             buf.values[t].copy_(value.reshape(shape))
-        self._last_value.copy_(self.ac.act(self._last_obs)[2])
+        self._last_value.copy_(self.ac.act(policy_input(T), **kw)[2])
 
     @torch.no_grad()
     def _collect_batched(self):
@@ -138,7 +150,7 @@ class PPO:
                 side = torch.cuda.Stream(self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
-                    self.ac.act(self._last_obs)
+                    self.ac.act(self._policy_in if self.obs_storage == "symbolic" else self._last_obs)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
