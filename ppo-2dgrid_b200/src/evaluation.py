@@ -19,9 +19,11 @@ from merlin_b200 import layouts as _layouts
 
 @torch.no_grad()
 def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=None, deterministic=True, poll=64,
-                   env=None, act_fn=None):
+                   env=None, act_fn=None, use_cuda_graph=True):
     """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)]).
-    `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` replaces `policy.act` (e.g. per-task adapted weights)."""
+    `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` replaces `policy.act` (e.g. per-task adapted weights).
+    A CNN policy acting by itself is evaluated in chunks of `poll` steps replayed from one CUDA graph (policy input
+    rendering, forward, argmax, env step, first-episode bookkeeping: no host work inside a chunk)."""
     from .actor_critic import CNNActorCritic
     seeds = [int(s) for s in seeds]
     B = len(seeds)
@@ -54,16 +56,37 @@ def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=Non
     elif act_fn is None:
         def act_fn(o):
             return policy.act(o, deterministic=deterministic)[0]
-    for t in range(env.max_steps):
+
+    def advance(obs):
         action = act_fn(obs)
         obs, _, term, _, info = env.step(action, frames=not lean)
         first = (info["episode_length"] > 0) & ~finished
-        ret = torch.where(first, info["episode_return"], ret)
-        length = torch.where(first, info["episode_length"], length)
-        goal |= first & term
-        finished |= first
-        if (t + 1) % poll == 0 and bool(finished.all()):
-            break
+        ret.copy_(torch.where(first, info["episode_return"], ret))
+        length.copy_(torch.where(first, info["episode_length"], length))
+        goal.logical_or_(first & term)
+        finished.logical_or_(first)
+        return obs
+
+    if lean and use_cuda_graph and dev.type == "cuda":
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator); acts, does not step
+            act_fn(None)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        chunk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(chunk):
+            for _ in range(poll):
+                advance(None)
+        # every env's first episode ends by max_steps; steps replayed beyond that only touch already finished envs
+        for _ in range((env.max_steps + poll - 1) // poll):
+            chunk.replay()
+            if bool(finished.all()):
+                break
+    else:
+        for t in range(env.max_steps):
+            obs = advance(obs)
+            if (t + 1) % poll == 0 and bool(finished.all()):
+                break
     policy.train(was_training)
     return ret.double().cpu().numpy(), length.long().cpu().numpy(), goal.cpu().numpy()
 

@@ -327,6 +327,12 @@ def test_batched_evaluation_matches_sequential_reference_loop():
     policy = CNNActorCritic((56, 56, 3), 3).to("cuda:0")
     seeds = [200000, 200001, 200002, 7, 8]
     ret, length, goal = evaluate_seeds(policy, "medium", 8, seeds, device="cuda:0", poll=16)
+    # the same evaluation stepped eagerly (no CUDA graph), and through the frame path (a caller-supplied act_fn)
+    ret_e, length_e, goal_e = evaluate_seeds(policy, "medium", 8, seeds, device="cuda:0", poll=16, use_cuda_graph=False)
+    ret_f, length_f, goal_f = evaluate_seeds(policy, "medium", 8, seeds, device="cuda:0", poll=16,
+                                             act_fn=lambda o: policy.act(o, deterministic=True)[0])
+    for other in ((ret_e, length_e, goal_e), (ret_f, length_f, goal_f)):
+        assert np.array_equal(other[1], length) and np.allclose(other[0], ret) and np.array_equal(other[2], goal)
     for k, s in enumerate(seeds):
         env = mr.make_env("medium", size=8)
         obs, _ = env.reset(seed=s)
