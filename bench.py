@@ -401,6 +401,27 @@ def run_ours(args):
                        "value_serial": world * N * e2e["steps"] / e2e_serial_s,
                        "value_obs_to_host": world * N * e2e["steps_obs"] / e2e_obs_s,
                        "d2h_bytes_per_step_obs_to_host": N * (56 * 56 * 3 + 4)}
+    if not args.skip_e2e:
+        # second data point, this rank's GPU only: the same path with gen_obs's own observation (7x7x3 symbolic image,
+        # 449 algorithmic B/step) instead of the wrapper's RGB frame -- the instruction-bound end of the path
+        senv = BatchedMerlinEnv(N, cells, agent, width=SIZE, height=SIZE, device=dev, want_rgb=False, want_symbolic=True)
+        senv.reset()
+        for i in range(W):
+            senv.step(acts[i % ring])
+        torch.cuda.synchronize(dev)
+        Ks = min(K, 512)
+        e0.record()
+        for i in range(Ks):
+            senv.step(acts[i % ring])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sms = e0.elapsed_time(e1) / Ks
+        sym_bytes = 147 + SIZE * SIZE + 32 + 8 + 6
+        line["symbolic_only"] = {"value_per_gpu": N / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "steps": Ks,
+                                 "kernel": senv.step_kernel(), "algorithmic_bytes_per_env_step": sym_bytes,
+                                 "roofline_frac": sym_bytes * N / (sms * 1e-3) / 1e9 / peak,
+                                 "note": "ALU-bound (ncu: IPC 2.15, 20 % DRAM): the layout pool is L2-resident, ~160 B/step reach DRAM"}
+        del senv
     if not args.skip_cpu_baseline:
         ref = CpuReference()
         n, dt = ref.run(200)
