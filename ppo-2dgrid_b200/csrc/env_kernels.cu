@@ -593,14 +593,14 @@ __global__ void __launch_bounds__(128, SWAR ? MERLIN_SYM_MINB : 1) env_kernel_sy
     emit_sym_rows(p.obs_sym + (size_t)e0 * kSymBytes, sym_s, min(32, p.N - e0), render_mask, lane, 32);
 }
 
-// Observation path.  Measured on B200 at 1M envs: the row-parallel form (obs_swar.cuh, 30 % fewer instructions, 56
-// instead of 72 registers) lifts the symbolic-only kernel from 7.1e9 to 1.07e10 env-steps/s (0.49 -> 0.73 of the HBM
-// roofline of its 449 B/step): that kernel is instruction-bound and runs 32 warps per SM.  The tile kernel gets SLOWER
-// with it (1.08 -> 1.01 of the copy peak): there ONE warp per CTA runs the state phase while three wait, so what
-// counts is that warp's latency, and the per-cell form's 49 independent loads / cells have more instruction-level
-// parallelism than the dependent 64-bit shift / multiply chains of the row form.  The ordered-group kernel is
-// indifferent (1.05 either way).  Hence: 0 = automatic = row-parallel in the symbolic-only kernel only,
-// 1 = per-cell everywhere, 2 = row-parallel in every kernel that has it (symbolic-only, tile, ordered; tests, A/B).
+// Observation path.  Measured on B200 at 1M envs: the row-parallel form (obs_swar.cuh, 30 % fewer instructions, 48
+// instead of 72 registers) lifts the symbolic-only kernel from 7.6e9 to 1.19e10 env-steps/s (0.52 -> 0.82 of the HBM
+// roofline of its 449 B/step): that kernel is ALU-bound and runs 40 warps per SM.  The frame kernels are indifferent
+// (tile kernel 1.083 per-cell vs 1.076 row form, ordered-group kernel 1.05 either way): their limit is the store
+// stream.  (With the window loads behind per-row branches the tile kernel dropped to 1.01 -- its single state-phase
+// warp paid one L2 round trip per row; window_rows() is straight-line for that reason.)  Hence: 0 = automatic =
+// row-parallel in the symbolic-only kernel only, 1 = per-cell everywhere, 2 = row-parallel in every kernel that has it
+// (symbolic-only, tile, ordered; tests, A/B).
 static int g_observation_path = 0;
 void set_observation_path(int path) { g_observation_path = path; }
 static bool use_swar(const EnvParams& p, bool frame_kernel) {

@@ -46,20 +46,40 @@ MERLIN_HD uint64_t bswap64(uint64_t x) {
 #endif
 }
 
-// Bytes x0 .. x0+6 of grid row `wy` (codes; CODE_WALL outside the grid), byte u at bits 8u.  Needs W >= 7 and an
-// 8-byte aligned `grid`.  Only bytes of this row's own cells are ever addressed (the second load is skipped unless the
-// seven cells straddle an 8-byte boundary), so nothing outside the grid's allocation is read.
-MERLIN_HD uint64_t window_row(const uint8_t* grid, int W, int H, int x0, int wy, uint64_t col_valid) {
-  if ((unsigned)wy >= (unsigned)H) return kWall7;
+// The seven window rows: r[v] = codes of cells (x0 .. x0+6, y0 + v), byte u at bits 8u, CODE_WALL outside the grid.
+// Needs W >= 7 and an 8-byte aligned `grid`.  Straight-line on purpose: all fourteen loads (two aligned 64-bit words
+// per row; the second repeats the first when the seven cells do not straddle an 8-byte boundary) are independent of any
+// branch, so they are in flight together -- with the loads behind per-row branches a lone warp pays one L2 round trip
+// per row.  Every address lies inside [0, cell_stride) of this grid: a row outside the grid reads row 0 instead and is
+// replaced by walls afterwards, and the second word ends at most at the next multiple of 8 after the row's last cell.
+MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, uint64_t (&r)[8]) {
   const int x0c = x0 < 0 ? 0 : (x0 > W - kView ? W - kView : x0);
-  const int base = wy * W + x0c;
-  const int a0 = base & ~7, sh = (base & 7) * 8;
-  uint64_t v = ld64(grid + a0) >> sh;
-  if (sh > 8) v |= ld64(grid + a0 + 8) << (64 - sh);
-  const int d = x0c - x0;                       // > 0: window starts left of the grid, < 0: ends right of it
-  if (d > 0) v <<= 8 * d;
-  else if (d < 0) v >>= 8 * (-d);
-  return (v & col_valid) | (kWall7 & ~col_valid);
+  const int d = x0c - x0;                        // > 0: the window starts left of the grid, < 0: it ends right of it
+  const int shl = d > 0 ? 8 * d : 0, shr = d < 0 ? -8 * d : 0;
+  uint64_t col_valid = 0;
+#pragma unroll
+  for (int u = 0; u < kView; ++u)
+    if ((unsigned)(x0 + u) < (unsigned)W) col_valid |= 0xffull << (8 * u);
+  uint64_t lo[kView], hi[kView];
+  int sh[kView];
+#pragma unroll
+  for (int v = 0; v < kView; ++v) {
+    const int wy = y0 + v;
+    const int base = ((unsigned)wy < (unsigned)H ? wy : 0) * W + x0c;
+    const int a0 = base & ~7;
+    sh[v] = (base & 7) * 8;
+    lo[v] = ld64(grid + a0);
+    hi[v] = ld64(grid + (sh[v] > 8 ? a0 + 8 : a0));
+  }
+#pragma unroll
+  for (int v = 0; v < kView; ++v) {
+    uint64_t x = lo[v] >> sh[v];
+    if (sh[v] > 8) x |= (hi[v] << 1) << (63 - sh[v]);
+    x = (x << shl) >> shr;
+    x = (x & col_valid) | (kWall7 & ~col_valid);
+    r[v] = (unsigned)(y0 + v) < (unsigned)H ? x : kWall7;
+  }
+  r[7] = 0;
 }
 
 // 8x8 byte-matrix transpose: r[i] byte j <-> r[j] byte i.
@@ -126,14 +146,8 @@ MERLIN_HD void observe_swar(const EnvState& s, const uint8_t* grid, int W, int H
   // window origin: get_view_exts
   const int x0 = s.dir == 0 ? s.x : (s.dir == 2 ? s.x - (kView - 1) : s.x - kView / 2);
   const int y0 = s.dir == 1 ? s.y : (s.dir == 3 ? s.y - (kView - 1) : s.y - kView / 2);
-  uint64_t col_valid = 0;
-#pragma unroll
-  for (int u = 0; u < kView; ++u)
-    if ((unsigned)(x0 + u) < (unsigned)W) col_valid |= 0xffull << (8 * u);
   uint64_t r[8];
-#pragma unroll
-  for (int v = 0; v < kView; ++v) r[v] = window_row(grid, W, H, x0, y0 + v, col_valid);
-  r[7] = 0;
+  window_rows(grid, W, H, x0, y0, r);
   // orientation: view (vi, vj) = window (u, v) with   dir 0: (6 - vj, vi)   dir 1: (6 - vi, 6 - vj)
   //                                                   dir 2: (vj, 6 - vi)   dir 3: (vi, vj)
   // i.e. g[vi] = rows (even dir) or columns (odd dir), bytes reversed for dir 0 / 1, index reversed for dir 1 / 2.
