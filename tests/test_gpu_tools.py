@@ -45,3 +45,4 @@ def test_bench_tool_small_batch():
                 "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e"):
         assert key in out, key
     assert out["gpu_launches"] == 16 and out["roofline"]["bound"] == "hbm" and out["e2e"]["h2d_bytes_per_step"] == 32768 * 8
+    assert "sym" in out["symbolic_only"]["kernel"] and out["symbolic_only"]["value_per_gpu"] > out["value"]
