@@ -72,9 +72,9 @@ class _ActorCriticBase(nn.Module):
     categorical-distribution formulas written out on tensors (no distribution object, no argument validation),
     so that a whole rollout can be captured in a CUDA graph without a host synchronisation."""
 
-    def forward(self, obs):
+    def forward(self, obs, **kw):
         """(logits `[B, A]`, value `[B]`) -- the functional entry point used for stacked per-task weights."""
-        return self._logits_value(obs)
+        return self._logits_value(obs, **kw)
 
     def act(self, obs, deterministic=False, **kw):
         logits, value = self._logits_value(obs, **kw)

@@ -123,8 +123,12 @@ class FOMAML:
         env.reset(out_obs=obs[0])
         # shared weights do not change during the rollout: form the re-indexed first-layer kernels once, not per step
         kw = {}
-        if params is None and self.use_cnn and getattr(policy, "blocked_first_layer", False):
-            kw["blocked"] = policy.blocked_weights()
+        if self.use_cnn and getattr(policy, "blocked_first_layer", False):
+            if params is None:
+                kw["blocked"] = policy.blocked_weights()
+            else:  # per-task weights: the stacked re-indexed kernels, one pair per task
+                kw["blocked"] = tuple(vmap(_blocked_kernel)(params[f"{trunk}_extractor.network.0.weight"])
+                                      for trunk in ("actor", "critic"))
         for t in range(steps):
             a, lp, v = self._act(policy, params, obs[t], **kw)
             env.step(a, out_obs=obs[t + 1], out=buf["rows"][t])
@@ -171,7 +175,11 @@ class FOMAML:
         """Sampled action, its log-probability and the value for one frame per task."""
         if params is None:
             return policy.act(self._fmt(obs), deterministic=False, **kw)
-        logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
+        if "blocked" in kw:
+            logits, value = vmap(lambda p, o, wa, wc: _logits_value(policy, p, o.unsqueeze(0), blocked=(wa, wc)))(
+                params, self._fmt(obs), *kw["blocked"])
+        else:
+            logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
         logits, value = logits.squeeze(1), value.squeeze(1)
         logp_all = torch.log_softmax(logits, dim=-1)
         a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
@@ -344,9 +352,15 @@ def _stack(policy, B):
             for n, p in policy.named_parameters()}
 
 
-def _logits_value(policy, params, obs):
+def _logits_value(policy, params, obs, **kw):
     """`policy._logits_value(obs)` evaluated with `params` substituted for the module's own weights."""
-    return functional_call(policy, params, (obs,))
+    return functional_call(policy, params, (obs,), kw)
+
+
+def _blocked_kernel(conv1_weight):
+    """One task's first-layer kernel re-indexed for space-to-depth input (CNNFeatureExtractor.blocked_weight)."""
+    from .actor_critic import _space_to_depth4_weight
+    return _space_to_depth4_weight(conv1_weight) * (1.0 / 255.0)
 
 
 def _clip_coef(grads, max_norm):
