@@ -16,6 +16,11 @@
  *   merlin_env_step               env.step(a)   src/ppo.py:76 ; src/fomaml.py:71 -- through
  *                                 ThreeActionWrapper (src/wrappers/three_action_wrapper.py:10-17),
  *                                 optionally StuckPenaltyWrapper (src/wrappers/stuck_penalty_wrapper.py:29-58)
+ *   merlin_env_policy_step        the whole rollout transition "act -> sample -> step -> store": Categorical(logits).sample(),
+ *                                 .log_prob(a) (src/actor_critic.py:80-99 act()), env.step(a) and RolloutBuffer.add /
+ *                                 the trajectory lists (src/ppo.py:70-86 ; src/fomaml.py:65-84) in ONE launch; with
+ *                                 `greedy` + the first-episode record it is one step of the deterministic evaluation
+ *                                 loops (ppo/ppo_train.py:43-69 ; src/sweep_checkpoints.py:58-78)
  *   merlin_env_render             RGBImgPartialObsWrapper.observation on stored symbolic observations (batched,
  *                                 gathered) -- the read side of a compact RolloutBuffer (src/rollout_buffer.py:3-32)
  *   merlin_env_render_f32         the same, written as the float32 `x / 255.0` tensor CNNFeatureExtractor.forward
@@ -30,9 +35,16 @@
  *     and copy.  Env state lives in device memory owned by the handle.
  *   - reset/step/gae are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
  *     legacy default stream), allocate nothing, never synchronise, and may be captured in a CUDA graph.
- *   - A handle is not thread-safe; one caller thread per handle.  One handle per device.  Calls on one handle must be
- *     stream-ordered with respect to each other (reset/step share an in-kernel tile scheduler, so do concurrent
- *     merlin_env_render calls): use one stream per handle, or order streams with events.
+ *   - A handle is not thread-safe: one caller thread per handle at a time.  Any number of handles may live in one
+ *     process, on the same or on different devices, each driven by its own thread; nothing in the library is shared
+ *     between handles except the two process-wide DEFAULTS of the tuning knobs below.
+ *   - Launches of one handle are stream-ordered: reset/step (which own the env state) and the render calls draw work
+ *     tickets from handle-owned counters.  On one stream nothing needs doing.  When a call arrives on a different
+ *     stream than the previous call of its kind, the library orders the new stream after the old one with an event
+ *     (eager launches only).  CUDA-graph replays are invisible to it: order a replay against eager calls on other
+ *     streams yourself.  Consecutive render launches use different counters, so a render may overlap a step.
+ *   - If a launch ever fails, the ticket counters are cleared on the failing call's stream; merlin_env_rearm() does the
+ *     same on demand (e.g. after a device-side fault was cleared by the application).
  *   - There is no CPU fallback: without a CUDA device every entry point fails with MERLIN_ECUDA.
  *
  * Packed cell code (1 byte per grid cell, row-major [y*W + x]):
@@ -58,7 +70,9 @@ extern "C" {
 
 /* flags for merlin_env_create */
 #define MERLIN_F_AUTO_RESET 0x1u      /* finished envs restart inside step(); obs is the new episode's */
-#define MERLIN_F_RESET_SAME 0x2u      /* restart on the SAME layout (FOMAML, src/fomaml.py:92); default: advance cursor by n_envs */
+#define MERLIN_F_RESET_SAME 0x2u      /* restart on the SAME layout (FOMAML, src/fomaml.py:92); default: move on by n_envs pool
+                                         slots modulo the pool size -- by ONE slot when the pool size divides n_envs, so that a
+                                         restart always brings a different layout */
 #define MERLIN_F_SEVEN_ACTIONS 0x4u   /* full MiniGrid action set 0..6; default: ThreeActionWrapper {left,right,forward} */
 #define MERLIN_F_STUCK_PENALTY 0x8u   /* StuckPenaltyWrapper semantics (off in the reference's training path) */
 #define MERLIN_F_EXPLORE_BONUS 0x10u  /* first-visit-per-episode bonus (not in the reference; builder-specified) */
@@ -126,6 +140,43 @@ int merlin_env_reset(merlin_env_t* h, const uint8_t* mask, uint8_t* obs_rgb, uin
 int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
                     uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream);
 
+/* Policy outputs in, sampled actions out: one rollout transition in one launch.  All pointers DEVICE.
+ *   logits      f32[N][A]  the actor head's output (A = 3, or 7 with MERLIN_F_SEVEN_ACTIONS); row e starts at
+ *                          logits + e * logits_stride floats (logits_stride = 0 means A: dense rows)
+ *   value       f32[N]     the critic's output, or NULL; element e at value + e * value_stride (0 means 1: dense) -- the
+ *                          strides let both heads be slices of ONE fused output matrix
+ *   action      i64[N]     OUT the action taken (row t of the rollout's action tensor)
+ *   logprob     f32[N]     OUT log_softmax(logits)[action] in float32: (l_a - max) - log(sum exp(l - max))
+ *   value_out   f32[N]     OUT copy of `value` (row t of the rollout's value tensor), or NULL
+ *   greedy      0: sample from Categorical(logits); 1: argmax (first maximum), the deterministic evaluation policy
+ *   finished / first_return / first_length / first_goal   u8 / f32 / i32 / u8 [N], all or none: the first-episode record
+ *               of an evaluation sweep ("freeze after done"): when env e ends an episode and finished[e] == 0, its return,
+ *               length and goal flag are stored and finished[e] becomes 1; later episodes of that env change nothing.
+ * Sampling is specified, not borrowed (torch's generator stream cannot be reproduced): u = Philox4x32-10(key = sampler
+ * seed, counter = (env, number of draws env has made, 0, 0)) word 0, top 24 bits; the action is the first a with
+ * cumsum(exp(l - max))[a] > u * sum, in float32, left to right.  Draw numbers advance by one per sampled step and are
+ * reset by merlin_env_seed_sampler (synchronous).  The result does not depend on the kernel mapping. */
+typedef struct merlin_policy_io {
+  const float* logits;
+  const float* value;
+  int64_t* action;
+  float* logprob;
+  float* value_out;
+  int32_t greedy;
+  int32_t logits_stride;
+  int32_t value_stride;
+  uint8_t* finished;
+  float* first_return;
+  int32_t* first_length;
+  uint8_t* first_goal;
+} merlin_policy_io_t;
+int merlin_env_policy_step(merlin_env_t* h, const merlin_policy_io_t* policy, uint8_t* obs_rgb, uint8_t* obs_sym,
+                           float* reward, uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras,
+                           void* stream);
+int merlin_env_seed_sampler(merlin_env_t* h, uint64_t seed);
+/* Clear the in-kernel work-ticket counters of this handle on `stream` (see Conventions). */
+int merlin_env_rearm(merlin_env_t* h, void* stream);
+
 /* Frames from STORED symbolic observations -- RGBImgPartialObsWrapper.observation (get_frame(tile_size=8,
  * agent_pov=True), src/scenario_creator/scenario_creator.py:48) as a batch op with an optional row gather, so a
  * rollout can keep the 147-byte symbolic image per step and expand minibatches on read (the reference's RolloutBuffer
@@ -157,14 +208,23 @@ int merlin_env_state_ptrs(merlin_env_t* h, int32_t** state_xyds /* int4[N]: pose
 /* Synchronous copy of the env state to HOST buffers (any may be NULL): state i32[N][4], cells u8[N][H*W]
  * (fails with MERLIN_ESTATE when grids are immutable -- index the pool by state[e][2] instead), episode_return f32[N]. */
 int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float* episode_return);
+/* The inverse: overwrite the env state from HOST buffers laid out as merlin_env_read_state returns them (any may be NULL)
+ * -- resume a saved rollout state, or start a benchmark from staggered episode clocks.  Synchronous; validated (poses
+ * inside the grid, layout indices inside the pool, 0 <= step_count < max_steps).  The next step()'s observation is
+ * computed from the new state; the observation buffers themselves are not touched. */
+int merlin_env_write_state(merlin_env_t* h, const int32_t* state, const uint8_t* cells, const float* episode_return);
 int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count); /* synchronises the device */
 int64_t merlin_env_launch_count(merlin_env_t* h);             /* kernels launched so far by this handle */
-/* Tuning/testing knob, process-wide: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
+/* Per-handle tuning knobs: same values as the two process-wide knobs below, or -1 = follow the process-wide default
+ * (the initial state of every handle). */
+int merlin_env_set_kernel_choice(merlin_env_t* h, int choice);
+int merlin_env_set_observation_path(merlin_env_t* h, int path);
+/* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
  * 3 = CTA-tile kernel, 4 = CTA-tile kernel with the frames stored by the TMA unit (cp.async.bulk), 5 = symbolic-only
  * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out.
  * All kernels produce identical results for the outputs they write; "automatic" never picks 4 or 6 (measured slower). */
 int merlin_set_kernel_choice(int choice);
-/* Tuning/testing knob, process-wide: how gen_obs is computed.  0 = automatic (default): the symbolic-only kernel works
+/* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: how gen_obs is computed.  0 = automatic (default): the symbolic-only kernel works
  * on seven window cells per 64-bit register (csrc/obs_swar.cuh; grids at least 7 wide), the frame kernels cell by cell
  * (csrc/env_logic.cuh) -- the faster choice for each, measured;  1 = cell by cell everywhere;  2 = the row-parallel form
  * in every kernel that has it (symbolic-only, tile, ordered).  Identical results. */

@@ -155,7 +155,9 @@ class OracleVecEnv:
         self.visited[idx, self.ay[idx] * self.W + self.ax[idx]] = True
         self.ep_return[idx] = 0
         if self.reset_mode == "next":
-            self.cursor[idx] = ((cur.astype(np.int64) + self.N) % self.L).astype(np.int32)
+            # a restart moves on by N pool slots (mod L), or by one slot when L divides N: always a different layout
+            stride = self.N % self.L or (1 if self.L > 1 else 0)
+            self.cursor[idx] = ((cur.astype(np.int64) + stride) % self.L).astype(np.int32)
 
     def observe(self, want_sym=True, want_rgb=None):
         want_rgb = self.want_rgb if want_rgb is None else want_rgb

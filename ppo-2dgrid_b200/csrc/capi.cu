@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -39,6 +40,14 @@ struct DeviceGuard {  // the caller (e.g. torch) owns the current-device setting
   }
 };
 
+// process-wide DEFAULTS of the two tuning knobs (merlin_set_kernel_choice / merlin_set_observation_path): what a handle
+// uses until merlin_env_set_kernel_choice / merlin_env_set_observation_path give it a setting of its own
+std::atomic<int> g_default_kernel_choice{0};
+std::atomic<int> g_default_observation_path{0};
+
+constexpr int kRenderRing = 16;                    // ticket-counter pairs the render launches rotate through
+constexpr int kSchedWords = 2 * (1 + kRenderRing); // pair 0: step / reset; pairs 1..16: render
+
 }  // namespace
 
 struct merlin_env {
@@ -52,6 +61,18 @@ struct merlin_env {
   int n_present = kAtlasTiles;           // atlas slots the current layout pool can show (host copy of the popcount)
   bool was_reset = false;
   int64_t launches = 0;
+  // per-handle tuning knobs (-1 = follow the process-wide default) and occupancy cache
+  int kernel_choice = -1;
+  int observation_path = -1;
+  int occ[kOccSlots] = {};
+  // action sampler (merlin_env_policy_step)
+  uint64_t sampler_seed = 0x9E3779B97F4A7C15ull;
+  uint32_t* draws = nullptr;             // [N] draws made so far per env
+  // stream ordering of the launches that share a ticket counter: class 0 = reset / step, class 1 = render
+  cudaStream_t last_stream[2] = {nullptr, nullptr};
+  bool last_stream_valid[2] = {false, false};
+  cudaEvent_t order_event = nullptr;
+  unsigned render_seq = 0;
   // device memory
   int4* state = nullptr;
   float* ep_return = nullptr;
@@ -79,13 +100,60 @@ static EnvParams base_params(const merlin_env* h) {
   p.N = h->cfg.n_envs; p.W = h->cfg.width; p.H = h->cfg.height; p.max_steps = h->cfg.max_steps;
   p.cell_stride = h->cell_stride; p.n_layouts = h->n_layouts; p.vis_words = h->vis_words;
   p.stuck_max_stay = h->cfg.stuck_max_stay; p.flags = h->cfg.flags;
+  // every restart must bring a different layout when the pool has more than one: N mod L, or 1 when L divides N
+  p.cursor_stride = h->n_layouts > 0 ? p.N % h->n_layouts : 0;
+  if (p.cursor_stride == 0 && h->n_layouts > 1) p.cursor_stride = 1;
   p.stuck_penalty = h->cfg.stuck_penalty; p.explore_bonus = h->cfg.explore_bonus;
   p.state = h->state; p.ep_return = h->ep_return; p.cells = h->cells; p.visited = h->visited;
   p.pool_cells = h->pool_cells; p.pool_agent = h->pool_agent; p.atlas = h->atlas; p.bad_actions = h->bad_actions;
   p.blit_lut = h->blit_lut;
   p.tile_present = h->tile_present;
   p.sched = h->sched;
+  p.draws = h->draws;
   return p;
+}
+
+static LaunchCtx launch_ctx(merlin_env* h) {
+  LaunchCtx c;
+  c.sm_count = h->sm_count;
+  c.kernel_choice = h->kernel_choice >= 0 ? h->kernel_choice : g_default_kernel_choice.load();
+  c.observation_path = h->observation_path >= 0 ? h->observation_path : g_default_observation_path.load();
+  c.occ = h->occ;
+  return c;
+}
+
+// Launches of one class (0 = reset / step, 1 = render) draw tickets from handle-owned counters, so they must not
+// overlap.  On one stream they cannot; when the caller moves to another stream, that stream is made to wait for
+// everything submitted to the previous one (an event recorded at its tail).  Streams under capture are left alone: the
+// captured graph's own dependencies order its launches, and replays are the caller's to order (header, "Conventions").
+static void order_streams(merlin_env* h, int cls, cudaStream_t s) {
+  if (h->last_stream_valid[cls] && h->last_stream[cls] != s && h->order_event) {
+    cudaStreamCaptureStatus a = cudaStreamCaptureStatusNone, b = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &a) == cudaSuccess && a == cudaStreamCaptureStatusNone &&
+        cudaStreamIsCapturing(h->last_stream[cls], &b) == cudaSuccess && b == cudaStreamCaptureStatusNone) {
+      if (cudaEventRecord(h->order_event, h->last_stream[cls]) == cudaSuccess) cudaStreamWaitEvent(s, h->order_event, 0);
+    }
+    cudaGetLastError();  // a stale stream handle is the caller's business; never leave an error behind
+  }
+  h->last_stream[cls] = s;
+  h->last_stream_valid[cls] = true;
+}
+
+static unsigned* render_sched(merlin_env* h) {
+  // consecutive render launches use different counter pairs: two renders that overlap on two streams (a policy-input
+  // render beside a minibatch render) would otherwise share one ticket counter
+  unsigned* s = h->sched + 2 * (1 + (h->render_seq % kRenderRing));
+  h->render_seq += 1;
+  return s;
+}
+
+// A launch that failed leaves the self-rearming ticket counters in an unknown state if an earlier kernel of this handle
+// died mid-flight: clear them (best effort, on the same stream) so the next launch does not silently skip tiles.
+static int launch_failed(merlin_env* h, cudaError_t err, const char* what, void* stream) {
+  cudaGetLastError();
+  cudaMemsetAsync(h->sched, 0, kSchedWords * sizeof(unsigned), static_cast<cudaStream_t>(stream));
+  cudaGetLastError();
+  return cuda_fail(err, what);
 }
 
 extern "C" {
@@ -128,40 +196,63 @@ int merlin_env_create(const merlin_env_config_t* cfg, merlin_env_t** out) {
   h->sm_count = prop.multiProcessorCount;
 
   const size_t N = (size_t)cfg->n_envs;
-  bool ok = true;
-  ok = ok && cudaMalloc(&h->state, N * sizeof(int4)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->ep_return, N * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->bad_actions, sizeof(unsigned long long)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->atlas, kAtlasBytes) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->sched, 4 * sizeof(unsigned)) == cudaSuccess;  // [0..1] step/reset, [2..3] render
-  ok = ok && cudaMalloc(&h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->atlas_blocked, kAtlasBytes) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->tile_present, 4 * sizeof(uint32_t)) == cudaSuccess;
-  if (ok && h->mutable_grid) ok = cudaMalloc(&h->cells, N * h->cell_stride) == cudaSuccess;
-  if (ok && (cfg->flags & MERLIN_F_EXPLORE_BONUS)) ok = cudaMalloc(&h->visited, N * h->vis_words * sizeof(uint32_t)) == cudaSuccess;
-  if (!ok) {
-    err = cudaGetLastError();
-    merlin_env_destroy(h);
-    return fail(MERLIN_ENOMEM, std::string("device allocation failed: ") + cudaGetErrorString(err));
-  }
-  cudaMemset(h->state, 0, N * sizeof(int4));
-  cudaMemset(h->ep_return, 0, N * sizeof(float));
-  cudaMemset(h->bad_actions, 0, sizeof(unsigned long long));
-  cudaMemset(h->atlas, 0, kAtlasBytes);
-  cudaMemset(h->sched, 0, 4 * sizeof(unsigned));
+  // every CUDA call of the set-up is checked; the first failure wins and the remaining steps are skipped
+  const char* what = "device allocation";
+  bool alloc_failed = false;
+  err = cudaSuccess;
+#define MERLIN_TRY(call, w)                                  \
+  do {                                                       \
+    if (err == cudaSuccess) {                                \
+      const cudaError_t e_ = (call);                         \
+      if (e_ != cudaSuccess) { err = e_; what = (w); }       \
+    }                                                        \
+  } while (0)
+#define MERLIN_ALLOC(ptr, bytes)                                              \
+  do {                                                                        \
+    if (err == cudaSuccess) {                                                 \
+      const cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));             \
+      if (e_ != cudaSuccess) { err = e_; what = "device allocation"; alloc_failed = true; } \
+    }                                                                         \
+  } while (0)
+  MERLIN_ALLOC(h->state, N * sizeof(int4));
+  MERLIN_ALLOC(h->ep_return, N * sizeof(float));
+  MERLIN_ALLOC(h->draws, N * sizeof(uint32_t));
+  MERLIN_ALLOC(h->bad_actions, sizeof(unsigned long long));
+  MERLIN_ALLOC(h->atlas, kAtlasBytes);
+  MERLIN_ALLOC(h->sched, kSchedWords * sizeof(unsigned));
+  MERLIN_ALLOC(h->blit_lut, kChunksPerLane * 32 * sizeof(uint32_t));
+  MERLIN_ALLOC(h->blit_lut_blocked, kChunksPerLane * 32 * sizeof(uint32_t));
+  MERLIN_ALLOC(h->atlas_blocked, kAtlasBytes);
+  MERLIN_ALLOC(h->tile_present, 4 * sizeof(uint32_t));
+  if (h->mutable_grid) MERLIN_ALLOC(h->cells, N * h->cell_stride);
+  if (cfg->flags & MERLIN_F_EXPLORE_BONUS) MERLIN_ALLOC(h->visited, N * h->vis_words * sizeof(uint32_t));
+  MERLIN_TRY(cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming), "event creation");
+  MERLIN_TRY(cudaMemset(h->state, 0, N * sizeof(int4)), "state init");
+  MERLIN_TRY(cudaMemset(h->ep_return, 0, N * sizeof(float)), "episode-return init");
+  MERLIN_TRY(cudaMemset(h->draws, 0, N * sizeof(uint32_t)), "sampler init");
+  MERLIN_TRY(cudaMemset(h->bad_actions, 0, sizeof(unsigned long long)), "counter init");
+  MERLIN_TRY(cudaMemset(h->atlas, 0, kAtlasBytes), "atlas init");
+  MERLIN_TRY(cudaMemset(h->sched, 0, kSchedWords * sizeof(unsigned)), "scheduler init");
   {
     uint32_t lut[kChunksPerLane * 32];
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut(c) : 0u;
-    cudaMemcpy(h->blit_lut, lut, sizeof lut, cudaMemcpyHostToDevice);
+    MERLIN_TRY(cudaMemcpy(h->blit_lut, lut, sizeof lut, cudaMemcpyHostToDevice), "blit map upload");
     for (int c = 0; c < kChunksPerLane * 32; ++c) lut[c] = c < kChunks ? chunk_lut_blocked(c) : 0u;
-    cudaMemcpy(h->blit_lut_blocked, lut, sizeof lut, cudaMemcpyHostToDevice);
-    cudaMemset(h->atlas_blocked, 0, kAtlasBytes);
-    cudaMemset(h->tile_present, 0xff, 4 * sizeof(uint32_t));
+    MERLIN_TRY(cudaMemcpy(h->blit_lut_blocked, lut, sizeof lut, cudaMemcpyHostToDevice), "blocked blit map upload");
+    MERLIN_TRY(cudaMemset(h->atlas_blocked, 0, kAtlasBytes), "blocked atlas init");
+    MERLIN_TRY(cudaMemset(h->tile_present, 0xff, 4 * sizeof(uint32_t)), "tile mask init");
   }
-  if (h->cells) cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride);
-  if (h->visited) cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t));
-  if ((err = cudaDeviceSynchronize()) != cudaSuccess) { merlin_env_destroy(h); return cuda_fail(err, "init"); }
+  if (h->cells) MERLIN_TRY(cudaMemset(h->cells, CODE_EMPTY, N * h->cell_stride), "grid init");
+  if (h->visited) MERLIN_TRY(cudaMemset(h->visited, 0, N * h->vis_words * sizeof(uint32_t)), "visited-map init");
+  MERLIN_TRY(cudaDeviceSynchronize(), "init");
+#undef MERLIN_TRY
+#undef MERLIN_ALLOC
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    merlin_env_destroy(h);
+    if (alloc_failed) return fail(MERLIN_ENOMEM, std::string("device allocation failed: ") + cudaGetErrorString(err));
+    return cuda_fail(err, what);
+  }
   *out = h;
   return MERLIN_OK;
 }
@@ -172,6 +263,8 @@ int merlin_env_destroy(merlin_env_t* h) {
   cudaFree(h->state); cudaFree(h->ep_return); cudaFree(h->cells); cudaFree(h->visited);
   cudaFree(h->pool_cells); cudaFree(h->pool_agent); cudaFree(h->atlas); cudaFree(h->bad_actions);
   cudaFree(h->blit_lut); cudaFree(h->blit_lut_blocked); cudaFree(h->atlas_blocked); cudaFree(h->tile_present); cudaFree(h->sched);
+  cudaFree(h->draws);
+  if (h->order_event) cudaEventDestroy(h->order_event);
   delete h;
   return MERLIN_OK;
 }
@@ -225,6 +318,7 @@ int merlin_env_upload_layouts(merlin_env_t* h, const uint8_t* cells, const int32
   if (err != cudaSuccess) return cuda_fail(err, "layout upload");
   h->n_present = count_present(present);
   h->was_reset = false;
+  cudaMemset(h->sched, 0, kSchedWords * sizeof(unsigned));  // the device is idle here: a cheap place to rearm the tickets
   return merlin_env_set_cursors(h, nullptr);
 }
 
@@ -333,17 +427,18 @@ int merlin_env_reset(merlin_env_t* h, const uint8_t* mask, uint8_t* obs_rgb, uin
   DeviceGuard guard(h->cfg.device);
   EnvParams p = base_params(h);
   p.reset_mask = mask; p.obs_rgb = obs_rgb; p.obs_sym = obs_sym;
-  cudaError_t err = launch_env_reset(p, h->sm_count, static_cast<cudaStream_t>(stream));
-  if (err != cudaSuccess) return cuda_fail(err, "env reset launch");
+  order_streams(h, 0, static_cast<cudaStream_t>(stream));
+  cudaError_t err = launch_env_reset(p, launch_ctx(h), static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return launch_failed(h, err, "env reset launch", stream);
   h->launches += 1;
   h->was_reset = true;
   return MERLIN_OK;
 }
 
-int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
-                    uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream) {
-  if (!h) return fail(MERLIN_EINVAL, "null handle");
-  if (!actions || !reward || !terminated || !truncated) return fail(MERLIN_EINVAL, "actions/reward/terminated/truncated are required");
+static int step_common(merlin_env_t* h, const int64_t* actions, const merlin_policy_io_t* pol, uint8_t* obs_rgb,
+                       uint8_t* obs_sym, float* reward, uint8_t* terminated, uint8_t* truncated,
+                       const merlin_step_extras_t* extras, void* stream) {
+  if (!reward || !terminated || !truncated) return fail(MERLIN_EINVAL, "reward/terminated/truncated are required");
   if (!h->was_reset) return fail(MERLIN_ESTATE, "step before reset");
   if (obs_rgb && !h->has_atlas) return fail(MERLIN_ESTATE, "RGB observation requested before the tile atlas was set");
   if (obs_rgb && (reinterpret_cast<uintptr_t>(obs_rgb) & 15)) return fail(MERLIN_EINVAL, "obs_rgb must be 16-byte aligned");
@@ -352,9 +447,59 @@ int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, u
   p.actions = actions; p.obs_rgb = obs_rgb; p.obs_sym = obs_sym;
   p.reward = reward; p.terminated = terminated; p.truncated = truncated;
   if (extras) { p.out_ep_return = extras->episode_return; p.out_ep_length = extras->episode_length; p.out_stuck = extras->stuck; p.out_done = extras->done; }
-  cudaError_t err = launch_env_step(p, h->sm_count, static_cast<cudaStream_t>(stream));
-  if (err != cudaSuccess) return cuda_fail(err, "env step launch");
+  if (pol) {
+    p.logits = pol->logits; p.value_in = pol->value; p.out_action = pol->action; p.out_logp = pol->logprob;
+    p.out_value = pol->value_out; p.greedy = pol->greedy ? 1 : 0;
+    p.logits_stride = pol->logits_stride > 0 ? pol->logits_stride : ((h->cfg.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3);
+    p.value_stride = pol->value_stride > 0 ? pol->value_stride : 1;
+    p.seed_lo = (uint32_t)h->sampler_seed; p.seed_hi = (uint32_t)(h->sampler_seed >> 32);
+    p.rec_finished = pol->finished; p.rec_return = pol->first_return; p.rec_length = pol->first_length;
+    p.rec_goal = pol->first_goal;
+  }
+  order_streams(h, 0, static_cast<cudaStream_t>(stream));
+  cudaError_t err = launch_env_step(p, launch_ctx(h), static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return launch_failed(h, err, "env step launch", stream);
   h->launches += 1;
+  return MERLIN_OK;
+}
+
+int merlin_env_step(merlin_env_t* h, const int64_t* actions, uint8_t* obs_rgb, uint8_t* obs_sym, float* reward,
+                    uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras, void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (!actions) return fail(MERLIN_EINVAL, "actions/reward/terminated/truncated are required");
+  return step_common(h, actions, nullptr, obs_rgb, obs_sym, reward, terminated, truncated, extras, stream);
+}
+
+int merlin_env_policy_step(merlin_env_t* h, const merlin_policy_io_t* pol, uint8_t* obs_rgb, uint8_t* obs_sym,
+                           float* reward, uint8_t* terminated, uint8_t* truncated, const merlin_step_extras_t* extras,
+                           void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (!pol || !pol->logits || !pol->action || !pol->logprob)
+    return fail(MERLIN_EINVAL, "merlin_env_policy_step: logits, action and logprob are required");
+  if (pol->value_out && !pol->value) return fail(MERLIN_EINVAL, "merlin_env_policy_step: value_out needs value");
+  if (pol->logits_stride < 0 || pol->value_stride < 0) return fail(MERLIN_EINVAL, "merlin_env_policy_step: negative stride");
+  if (pol->logits_stride > 0 && pol->logits_stride < ((h->cfg.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3))
+    return fail(MERLIN_EINVAL, "merlin_env_policy_step: logits_stride smaller than the action count");
+  if (pol->finished && (!pol->first_return || !pol->first_length || !pol->first_goal))
+    return fail(MERLIN_EINVAL, "merlin_env_policy_step: the first-episode record needs all four arrays");
+  return step_common(h, nullptr, pol, obs_rgb, obs_sym, reward, terminated, truncated, extras, stream);
+}
+
+int merlin_env_seed_sampler(merlin_env_t* h, uint64_t seed) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaDeviceSynchronize();  // no step may still be drawing
+  if (err == cudaSuccess) err = cudaMemset(h->draws, 0, (size_t)h->cfg.n_envs * sizeof(uint32_t));
+  if (err != cudaSuccess) return cuda_fail(err, "sampler reseed");
+  h->sampler_seed = seed;
+  return MERLIN_OK;
+}
+
+int merlin_env_rearm(merlin_env_t* h, void* stream) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaMemsetAsync(h->sched, 0, kSchedWords * sizeof(unsigned), static_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) return cuda_fail(err, "scheduler rearm");
   return MERLIN_OK;
 }
 
@@ -371,9 +516,10 @@ int merlin_env_render(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_rows, c
   p.atlas = blocked ? h->atlas_blocked : h->atlas;
   p.lut = blocked ? h->blit_lut_blocked : h->blit_lut;
   p.tile_present = h->tile_present;
-  p.sched = h->sched + 2;
+  p.sched = render_sched(h);
+  order_streams(h, 1, static_cast<cudaStream_t>(stream));
   cudaError_t err = launch_render(p, blocked != 0, h->sm_count, static_cast<cudaStream_t>(stream));
-  if (err != cudaSuccess) return cuda_fail(err, "render launch");
+  if (err != cudaSuccess) return launch_failed(h, err, "render launch", stream);
   h->launches += 1;
   return MERLIN_OK;
 }
@@ -391,11 +537,12 @@ int merlin_env_render_f32(merlin_env_t* h, const uint8_t* obs_sym, int64_t n_row
   p.sym = obs_sym; p.index = index; p.out_f32 = out; p.M = m; p.n_rows = n_rows;
   p.atlas = h->atlas_blocked;
   p.tile_present = h->tile_present;
-  p.sched = h->sched + 2;
+  p.sched = render_sched(h);
   p.normalise = normalise;
   p.cap_tiles = h->n_present < 8 ? 8 : (h->n_present > kAtlasTiles ? kAtlasTiles : h->n_present);
+  order_streams(h, 1, static_cast<cudaStream_t>(stream));
   cudaError_t err = launch_render_f32(p, h->sm_count, static_cast<cudaStream_t>(stream));
-  if (err != cudaSuccess) return cuda_fail(err, "render_f32 launch");
+  if (err != cudaSuccess) return launch_failed(h, err, "render_f32 launch", stream);
   h->launches += 1;
   return MERLIN_OK;
 }
@@ -436,6 +583,37 @@ int merlin_env_read_state(merlin_env_t* h, int32_t* state, uint8_t* cells, float
   return MERLIN_OK;
 }
 
+int merlin_env_write_state(merlin_env_t* h, const int32_t* state, const uint8_t* cells, const float* episode_return) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (!h->was_reset) return fail(MERLIN_ESTATE, "write_state before the first reset");
+  if (cells && !h->cells) return fail(MERLIN_ESTATE, "grids are immutable: an env's grid is the pool entry state[e][2] names");
+  const size_t N = (size_t)h->cfg.n_envs;
+  const int W = h->cfg.width, H = h->cfg.height;
+  if (state) {
+    for (size_t e = 0; e < N; ++e) {
+      EnvState s{};
+      unpack_state(state[4 * e], state[4 * e + 1], state[4 * e + 2], state[4 * e + 3], s);
+      const int layout = s.layout < 0 ? ~s.layout : s.layout;
+      if (s.x >= W || s.y >= H || layout >= h->n_layouts || s.step_count < 0 || s.step_count >= h->cfg.max_steps) {
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "env %zu: state outside the grid / pool / episode (x %d y %d layout %d step_count %d)",
+                      e, s.x, s.y, layout, s.step_count);
+        return fail(MERLIN_EINVAL, msg);
+      }
+    }
+  }
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err == cudaSuccess && state) err = cudaMemcpy(h->state, state, N * sizeof(int4), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && episode_return) err = cudaMemcpy(h->ep_return, episode_return, N * sizeof(float), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && cells) {
+    const size_t HW = (size_t)W * H;
+    err = cudaMemcpy2D(h->cells, h->cell_stride, cells, HW, HW, N, cudaMemcpyHostToDevice);
+  }
+  if (err != cudaSuccess) return cuda_fail(err, "state write");
+  return MERLIN_OK;
+}
+
 int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count) {
   if (!h || !count) return fail(MERLIN_EINVAL, "null argument");
   DeviceGuard guard(h->cfg.device);
@@ -449,20 +627,43 @@ int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count) {
 int64_t merlin_env_launch_count(merlin_env_t* h) { return h ? h->launches : 0; }
 
 const char* merlin_env_step_kernel(merlin_env_t* h, int rgb) {
-  return h ? step_kernel_name(h->cfg.n_envs, rgb != 0, h->sm_count) : "";
+  return h ? step_kernel_name(h->cfg.n_envs, rgb != 0, launch_ctx(h)) : "";
+}
+
+static int check_kernel_choice(int choice, int lowest) {
+  if (choice < lowest || choice > 6)
+    return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile), 4 (tile, TMA frame stores), 5 (symbolic-only) or 6 (ordered groups)");
+  return MERLIN_OK;
+}
+static int check_observation_path(int path, int lowest) {
+  if (path < lowest || path > 2)
+    return fail(MERLIN_EINVAL, "observation path must be 0 (automatic), 1 (per-cell form) or 2 (row-parallel form wherever built)");
+  return MERLIN_OK;
 }
 
 int merlin_set_kernel_choice(int choice) {
-  if (choice < 0 || choice > 6)
-    return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile), 4 (tile, TMA frame stores), 5 (symbolic-only) or 6 (ordered groups)");
-  set_kernel_choice(choice);
+  if (int rc = check_kernel_choice(choice, 0)) return rc;
+  g_default_kernel_choice.store(choice);
   return MERLIN_OK;
 }
 
 int merlin_set_observation_path(int path) {
-  if (path < 0 || path > 2)
-    return fail(MERLIN_EINVAL, "observation path must be 0 (automatic), 1 (per-cell form) or 2 (row-parallel form wherever built)");
-  set_observation_path(path);
+  if (int rc = check_observation_path(path, 0)) return rc;
+  g_default_observation_path.store(path);
+  return MERLIN_OK;
+}
+
+int merlin_env_set_kernel_choice(merlin_env_t* h, int choice) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (int rc = check_kernel_choice(choice, -1)) return rc;
+  h->kernel_choice = choice;
+  return MERLIN_OK;
+}
+
+int merlin_env_set_observation_path(merlin_env_t* h, int path) {
+  if (!h) return fail(MERLIN_EINVAL, "null handle");
+  if (int rc = check_observation_path(path, -1)) return rc;
+  h->observation_path = path;
   return MERLIN_OK;
 }
 

@@ -43,15 +43,73 @@ __device__ __forceinline__ bool tile_bit(const uint32_t* m, int tile) {
   return (__ldg(m + (tile >> 5)) >> (tile & 31)) & 1u;
 }
 
+// Can a closed / locked door occur in a grid of this handle?  Read from the device-resident "present" mask (codes
+// type | colour << 4 with type 11 / 12; mutable grids set every bit), so a CUDA graph captured before a re-upload
+// still sees the current pool.  Without doors, walls are the only opaque cells and Grid.encode needs no state byte:
+// the row-parallel observation takes its short path (warp-uniform branch).
+__device__ __forceinline__ bool pool_has_doors(const uint32_t* present) {
+  constexpr uint32_t kDoorBits = (1u << T_DOOR_CLOSED) | (1u << T_DOOR_LOCKED);
+  constexpr uint32_t kMask = kDoorBits | (kDoorBits << 16);   // colours 2w and 2w + 1 share word w
+  return ((__ldg(present) | __ldg(present + 1) | __ldg(present + 2) | __ldg(present + 3)) & kMask) != 0;
+}
+
 struct Flags {
   int n_actions;
   bool mutable_grid, stuck_on, explore_on, auto_reset, advance, want_rgb, want_sym;
+  bool doors = true;   // set by the kernels that run the row-parallel observation
   __device__ __forceinline__ explicit Flags(const EnvParams& p)
       : n_actions((p.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3), mutable_grid(p.cells != nullptr),
         stuck_on(p.flags & MERLIN_F_STUCK_PENALTY), explore_on(p.flags & MERLIN_F_EXPLORE_BONUS),
         auto_reset(p.flags & MERLIN_F_AUTO_RESET), advance(!(p.flags & MERLIN_F_RESET_SAME)),
         want_rgb(p.obs_rgb != nullptr), want_sym(p.obs_sym != nullptr) {}
 };
+
+// The action env e takes this step: read from `actions`, or -- policy I/O -- drawn here from the policy's logits
+// (sample_policy, env_logic.cuh).  `commit`: this thread stores the action / log-probability / value rows and advances
+// the env's draw counter (one lane per env in the lane-per-env kernels, lane 0 in the warp-per-env kernel, where every
+// lane computes the same sample from the same warp-uniform loads).
+struct ActionDraw {
+  long long action;
+  float logp;
+  uint32_t draw;
+};
+__device__ __forceinline__ ActionDraw draw_action(const EnvParams& p, int n_actions, int e) {
+  ActionDraw d;
+  d.logp = 0.f;
+  d.draw = 0;
+  if (p.logits == nullptr) {
+    d.action = p.actions[e];
+    return d;
+  }
+  float lg[kMaxActions];
+  const float* row = p.logits + (size_t)e * p.logits_stride;
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? row[a] : 0.f;
+  float u = 0.f;
+  if (!p.greedy) {
+    d.draw = p.draws[e];
+    u = sampler_uniform(p.seed_lo, p.seed_hi, (uint32_t)e, d.draw);
+  }
+  const PolicySample smp = sample_policy(lg, n_actions, u, p.greedy != 0);
+  d.action = smp.action;
+  d.logp = smp.logp;
+  return d;
+}
+__device__ __forceinline__ void commit_action(const EnvParams& p, int e, const ActionDraw& d) {
+  if (p.logits == nullptr) return;
+  if (!p.greedy) p.draws[e] = d.draw + 1u;
+  p.out_action[e] = d.action;
+  p.out_logp[e] = d.logp;
+  if (p.out_value) p.out_value[e] = p.value_in[(size_t)e * p.value_stride];
+}
+// First-episode record of deterministic evaluation (see EnvParams::rec_finished).
+__device__ __forceinline__ void record_first_episode(const EnvParams& p, int e, bool done, bool goal, float ep_ret, int len) {
+  if (p.rec_finished == nullptr || !done || p.rec_finished[e]) return;
+  p.rec_finished[e] = 1;
+  p.rec_return[e] = ep_ret;
+  p.rec_length[e] = len;
+  p.rec_goal[e] = goal ? 1 : 0;
+}
 
 // Stage the tile atlas: only the slots a frame of this handle's layout pool can show (5 of 128 for the MERLIN
 // scenarios: 960 B instead of 24 KB), at their usual offsets.  All threads of the CTA take part.
@@ -107,7 +165,7 @@ __device__ __forceinline__ void emit_sym_rows(uint8_t* out, const uint8_t* sym_s
 // (any alignment: rows of consecutive lanes are 147 bytes apart).  The image is assembled as 37 little-endian words in
 // registers, funnel-shifted by this lane's misalignment and stored as 35 aligned words; the words that straddle the
 // row's two ends are shared with the neighbouring lanes' rows and go out as single bytes.
-__device__ __forceinline__ void store_sym_row(uint8_t* row, const uint64_t (&g)[kView]) {
+__device__ __forceinline__ void store_sym_row(uint8_t* row, const uint64_t (&g)[kView], bool doors) {
   uint32_t r[38];
   {
     uint64_t acc = 0;
@@ -115,7 +173,7 @@ __device__ __forceinline__ void store_sym_row(uint8_t* row, const uint64_t (&g)[
 #pragma unroll
     for (int vi = 0; vi < kView; ++vi) {
       uint32_t w[6];
-      encode_group(g[vi], w);
+      encode_group(g[vi], w, doors);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         acc |= (uint64_t)w[i] << (8 * have);
@@ -171,7 +229,9 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
       const int fidx = fy * p.W + fx;
       const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
-      StepResult r = step_logic(s, p.actions[e], f.n_actions, fwd, inb, fidx, p.max_steps);
+      const ActionDraw act = draw_action(p, f.n_actions, e);
+      commit_action(p, e, act);
+      StepResult r = step_logic(s, act.action, f.n_actions, fwd, inb, fidx, p.max_steps);
       if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
       if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
 
@@ -193,7 +253,8 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       if (p.out_ep_return) p.out_ep_return[e] = done ? ep_ret : 0.f;
       if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
       if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
-        if (p.out_done) p.out_done[e] = done ? 1.f : 0.f;
+      if (p.out_done) p.out_done[e] = done ? 1.f : 0.f;
+      record_first_episode(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
       restart = done && f.auto_reset;
     }
   } else {
@@ -207,7 +268,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
   if (restart_mask) {
     // pool index this env loads: pending first layout, else the next (PPO) or the same (FOMAML) one
     const int load_cur = s.layout < 0 ? ~s.layout
-                                      : (f.advance ? (int)(((long long)s.layout + p.N) % p.n_layouts) : s.layout);
+                                      : (f.advance ? (int)(((unsigned)s.layout + (unsigned)p.cursor_stride) % (unsigned)p.n_layouts) : s.layout);
     if (restart) {
       const uint32_t a = p.pool_agent[load_cur];
       s.x = a & 0xff; s.y = (a >> 8) & 0xff; s.dir = (a >> 16) & 3; s.carry = 0;
@@ -252,7 +313,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
     uint8_t* kind = kinds_s + lane * kKindStride;
     if (SWAR) {
       uint64_t g[kView], seen[kView];
-      observe_swar(s, grid, p.W, p.H, g, seen);
+      observe_swar(s, grid, p.W, p.H, g, seen, f.doors);
       if (f.want_rgb) {
         uint32_t kw[13];
         kind_words(g, s.carry, kw);
@@ -260,7 +321,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
 #pragma unroll
         for (int i = 0; i < 13; ++i) kdst[i] = kw[i];
       }
-      if (f.want_sym) store_sym_row(sym_s + lane * kSymBytes, g);
+      if (f.want_sym) store_sym_row(sym_s + lane * kSymBytes, g, f.doors);
     } else {
       const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
       const uint64_t vis = visibility(transp);
@@ -342,7 +403,8 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_ordered(const EnvPar
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const Flags f(p);
+  Flags f(p);
+  if (SWAR) f.doors = pool_has_doors(p.tile_present);
   uint8_t* atlas_s = smem;
   uint8_t* warp_s = smem + kAtlasBytes + warp * warp_smem_bytes(G);
   uint8_t* kinds_s = warp_s;
@@ -409,7 +471,8 @@ __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  const Flags f(p);
+  Flags f(p);
+  if (SWAR) f.doors = pool_has_doors(p.tile_present);
   uint8_t* atlas_s = smem;
   uint8_t* kinds_s = smem + kAtlasBytes;   // [T][kKindStride]
   uint8_t* sym_s = kinds_s + T * kKindStride;              // [T][147]
@@ -581,6 +644,7 @@ __global__ void __launch_bounds__(128, SWAR ? MERLIN_SYM_MINB : 1) env_kernel_sy
   const int warp = threadIdx.x >> 5;
   Flags f(p);
   f.want_rgb = false;  // no frame phase here: tile kinds are not produced either
+  if (SWAR) f.doors = pool_has_doors(p.tile_present);
   // the row-parallel form keeps the window in registers; only the per-cell form stages the 49 codes per env
   uint8_t* warp_s = smem + warp * sym_kernel_warp_smem(SWAR);
   uint8_t* kinds_s = SWAR ? nullptr : warp_s;
@@ -601,19 +665,17 @@ __global__ void __launch_bounds__(128, SWAR ? MERLIN_SYM_MINB : 1) env_kernel_sy
 // warp paid one L2 round trip per row; window_rows() is straight-line for that reason.)  Hence: 0 = automatic =
 // row-parallel in the symbolic-only kernel only, 1 = per-cell everywhere, 2 = row-parallel in every kernel that has it
 // (symbolic-only, tile, ordered; tests, A/B).
-static int g_observation_path = 0;
-void set_observation_path(int path) { g_observation_path = path; }
-static bool use_swar(const EnvParams& p, bool frame_kernel) {
-  if (p.W < kView || g_observation_path == 1) return false;
-  return g_observation_path == 2 || !frame_kernel;
+static bool use_swar(const EnvParams& p, const LaunchCtx& ctx, bool frame_kernel) {
+  if (p.W < kView || ctx.observation_path == 1) return false;
+  return ctx.observation_path == 2 || !frame_kernel;
 }
 
 template <bool STEP>
-static cudaError_t launch_sym_kernel(const EnvParams& p, cudaStream_t stream) {
+static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int threads = 128, warps = threads / 32;
   const int n_groups = (p.N + 31) / 32;
   const int grid = (n_groups + warps - 1) / warps;
-  if (use_swar(p, false))
+  if (use_swar(p, ctx, false))
     env_kernel_sym<STEP, true><<<grid, threads, warps * sym_kernel_warp_smem(true), stream>>>(p, n_groups);
   else
     env_kernel_sym<STEP, false><<<grid, threads, warps * sym_kernel_warp_smem(false), stream>>>(p, n_groups);
@@ -621,41 +683,81 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// env_kernel_warp<STEP>: one WARP per environment.
+// env_kernel_warp<STEP>: one WARP per environment -- the small-batch mapping (N <= 24 576: every env of the batch is
+// resident at once and the run time is launch latency + one env's dependent chain + the instructions issued per SM).
 //   * state / action / forward cell are loaded at warp-uniform addresses (one broadcast transaction each) and the
-//     step logic runs redundantly on all lanes; lane 0 alone writes the per-env outputs and the new state.
+//     step logic runs redundantly on all lanes; lane 0 alone writes the per-env outputs and the new state.  The first
+//     env's state and action are requested BEFORE the atlas is staged, so both round trips overlap.
 //   * the 49-cell window is gathered two cells per lane; transparency goes through two warp ballots into the same
 //     49-bit mask the visibility routine consumes; every lane then knows the visibility of its own cells.
+//   * frame phase without a blit map: the frame is 28 pairs of pixel rows; a pair is 336 bytes = 21 16-byte chunks, and
+//     chunk l of EVERY pair covers the same (cell column, tile part) twice over -- so lane l < 21 owns chunk l of all 28
+//     pairs, its two (vi, part) are loop constants, the tile row (vj, py) is the loop counter, and after unrolling
+//     every shared-memory and global address is `lane register + immediate`: 3 instructions per chunk (two 8-byte
+//     atlas reads, one 16-byte store) plus 4 per tile row for the two kinds, ~115 per frame instead of ~480 with the
+//     588-entry chunk map (ncu at 4096 envs, profiles/r02_warp_kernel_ncu.md: 1390 -> ~650 warp instructions per env).
+//     The kinds are kept premultiplied (kind * 192, the tile's byte offset in the atlas) as 16-bit words.
+//   * atlas staging touches only the slots the pool can show: thread t tests tile t / 2 and copies half of it.
 constexpr int kWarpKernelThreads = 256;
+constexpr int kWarpKindBytes = 128;          // 49 premultiplied kinds (u16) per warp, padded
+constexpr int kPairChunks = 2 * kUnitsPerRow / 2;   // 21 16-byte chunks per pair of pixel rows
+constexpr int kRowPairs = kView * kTile / 2;        // 28
 
-// The blit map lives in shared memory here (not in 19 registers per lane as in the other kernels): at the batch sizes
-// this kernel serves the run time is launch latency + the dependent-load chain of one env, not the store pipe, and
-// 56 registers let 3+ CTAs per SM hold every env of a <= 16k batch at once (measured: 28.7 vs 31.9 us at 16384 envs).
 template <bool STEP>
-__global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const EnvParams p) {
+__global__ void __launch_bounds__(kWarpKernelThreads, 4) env_kernel_warp(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const Flags f(p);
   uint8_t* atlas_s = smem;
-  uint8_t* kp = smem + kAtlasBytes + warp * kWarpKindStride;   // this warp's 49 tile kinds
+  uint16_t* kq = reinterpret_cast<uint16_t*>(smem + kAtlasBytes + warp * kWarpKindBytes);   // this warp's 49 kinds * 192
 
-  uint32_t* lut_s = reinterpret_cast<uint32_t*>(smem + kAtlasBytes + (blockDim.x >> 5) * kWarpKindStride);
+  int e = blockIdx.x * warps_per_cta + warp;
+  // first env's state / action: in flight while the atlas is staged
+  int4 st_next = make_int4(0, 0, 0, 0);
+  long long act_next = 0;
+  if (e < p.N) {
+    st_next = p.state[e];
+    if (STEP && p.logits == nullptr) act_next = p.actions[e];
+  }
   if (f.want_rgb) {
-    stage_atlas(p, atlas_s);
-    for (int i = threadIdx.x; i < kChunksPerLane * 32; i += blockDim.x) lut_s[i] = __ldg(p.blit_lut + i);
+    const int tile = threadIdx.x >> 1, half = threadIdx.x & 1;   // 256 threads = 128 tiles x 2 halves of 6 int4
+    if (tile < kAtlasTiles && tile_bit(p.tile_present, tile)) {
+      const int4* src = reinterpret_cast<const int4*>(p.atlas) + tile * (kTileBytes / 16) + half * 6;
+      int4* dst = reinterpret_cast<int4*>(atlas_s) + tile * (kTileBytes / 16) + half * 6;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) dst[i] = __ldg(src + i);
+    }
   }
   __syncthreads();
 
   // this lane's two window cells, in mask order c = vj*7 + vi
   const int c0 = lane, c1 = lane + 32;
-  const int vj0 = c0 / kView, vi0 = c0 - vj0 * kView;
-  const int vj1 = c1 < kCells ? c1 / kView : 0, vi1 = c1 < kCells ? c1 - vj1 * kView : 0;
+  const int vj0 = (c0 * 37) >> 8, vi0 = c0 - vj0 * kView;                       // c / 7 for c < 64
+  const int vj1 = c1 < kCells ? (c1 * 37) >> 8 : 0, vi1 = c1 < kCells ? c1 - vj1 * kView : 0;
+  const int a0 = (kView - 1) - vj0, b0 = vi0 - kView / 2, a1 = (kView - 1) - vj1, b1 = vi1 - kView / 2;
+  // frame phase constants of this lane: chunk `lane` of every row pair = units 2*lane and 2*lane + 1 of 42
+  const int u0 = 2 * lane, u1 = 2 * lane + 1;
+  const int r0 = u0 >= kUnitsPerRow, r1 = u1 >= kUnitsPerRow;          // second row of the pair?
+  const int w0 = u0 - r0 * kUnitsPerRow, w1 = u1 - r1 * kUnitsPerRow;
+  const int cv0 = (w0 * 11) >> 5, cv1 = (w1 * 11) >> 5;                 // w / 3 for w < 21: the cell column vi
+  const uint16_t* kq0 = kq + cv0 * kView;                               // + vj
+  const uint16_t* kq1 = kq + cv1 * kView;
+  const uint8_t* at0 = atlas_s + (w0 - 3 * cv0) * 8 + r0 * 24;          // + kind * 192 + (py & ~1) * 24
+  const uint8_t* at1 = atlas_s + (w1 - 3 * cv1) * 8 + r1 * 24;
 
-  for (int e = blockIdx.x * warps_per_cta + warp; e < p.N; e += gridDim.x * warps_per_cta) {
+  for (; e < p.N; e += gridDim.x * warps_per_cta) {
     EnvState s{};
-    const int4 st = p.state[e];
+    const int4 st = st_next;
+    const long long act_in = act_next;
+    {
+      const int en = e + gridDim.x * warps_per_cta;   // prefetch the next env of this warp
+      if (en < p.N) {
+        st_next = p.state[en];
+        if (STEP && p.logits == nullptr) act_next = p.actions[en];
+      }
+    }
     unpack_state(st.x, st.y, st.z, st.w, s);
     float ep_ret = p.ep_return[e];
     bool restart = false, render = true;
@@ -667,7 +769,10 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
       const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
       const int fidx = fy * p.W + fx;
       const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
-      StepResult r = step_logic(s, p.actions[e], f.n_actions, fwd, inb, fidx, p.max_steps);
+      ActionDraw act;
+      if (p.logits != nullptr) act = draw_action(p, f.n_actions, e);
+      else { act.action = act_in; act.logp = 0.f; act.draw = 0; }
+      StepResult r = step_logic(s, act.action, f.n_actions, fwd, inb, fidx, p.max_steps);
       uint32_t vword = 0;
       const int cell = s.y * p.W + s.x;
       uint32_t* vptr = nullptr;
@@ -679,8 +784,10 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
       const float rew = (float)rew_d;
       ep_ret += rew;
       const bool done = r.terminated || r.truncated;
-      __syncwarp();  // every lane has read the old grid cell / visited word before lane 0 overwrites them
+      __syncwarp();  // every lane has read the old grid cell / visited word / draw counter before lane 0 overwrites them
       if (lane == 0) {
+        commit_action(p, e, act);
+        record_first_episode(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
         if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
         if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
         if (f.explore_on && vword != vword_in) *vptr = vword;
@@ -700,7 +807,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
 
     if (restart) {  // warp-uniform
       const int load_cur = s.layout < 0 ? ~s.layout
-                                        : (f.advance ? (int)(((long long)s.layout + p.N) % p.n_layouts) : s.layout);
+                                        : (f.advance ? (int)(((unsigned)s.layout + (unsigned)p.cursor_stride) % (unsigned)p.n_layouts) : s.layout);
       const uint32_t a = p.pool_agent[load_cur];
       s.x = a & 0xff; s.y = (a >> 8) & 0xff; s.dir = (a >> 16) & 3; s.carry = 0;
       s.step_count = 0; s.stay = 0; s.last_x = s.x; s.last_y = s.y;
@@ -735,13 +842,11 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
     const int rx = -fy, ry = fx;
     uint32_t code0, code1 = CODE_WALL;
     {
-      const int a = (kView - 1) - vj0, b = vi0 - kView / 2;
-      const int wx = s.x + a * fx + b * rx, wy = s.y + a * fy + b * ry;
+      const int wx = s.x + a0 * fx + b0 * rx, wy = s.y + a0 * fy + b0 * ry;
       code0 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
     }
     if (c1 < kCells) {
-      const int a = (kView - 1) - vj1, b = vi1 - kView / 2;
-      const int wx = s.x + a * fx + b * rx, wy = s.y + a * fy + b * ry;
+      const int wx = s.x + a1 * fx + b1 * rx, wy = s.y + a1 * fy + b1 * ry;
       code1 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
     }
     const unsigned t0 = __ballot_sync(0xffffffffu, !((M_OPAQUE >> (code0 & 0xf)) & 1u));
@@ -758,7 +863,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
       const bool agent_cell = (vi == kView / 2 && vj == kView - 1);
       if (agent_cell) code = s.carry ? s.carry : CODE_EMPTY;
       const int k = vi * kView + vj;
-      kp[k] = (uint8_t)(agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN));
+      kq[k] = (uint16_t)((agent_cell ? agent_kind(s.carry) : (seen ? code : KIND_UNSEEN)) * kTileBytes);
       if (f.want_sym) {
         uint8_t t = 0, col = 0, stt = 0;
         if (seen) sym_of_code(code, t, col, stt);
@@ -766,22 +871,21 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 3) env_kernel_warp(const E
       }
     }
     __syncwarp();
-    if (f.want_rgb) {
-      const uint2* atlas64 = reinterpret_cast<const uint2*>(atlas_s);
-      uint8_t* frame = p.obs_rgb + (size_t)e * kImgBytes;
-#pragma unroll 4
-      for (int k = 0; k < kChunksPerLane; ++k) {
-        const int c = lane + 32 * k;
-        if (c < kChunks) {
-          const uint32_t q = lut_s[c];
-          const uint32_t k0 = kp[q & 0xff], k1 = kp[(q >> 16) & 0xff];
-          const uint2 a = atlas64[k0 * (kTileBytes / 8) + ((q >> 8) & 0xff)];
-          const uint2 b = atlas64[k1 * (kTileBytes / 8) + (q >> 24)];
-          st_stream_v4(frame + c * 16, a.x, a.y, b.x, b.y);
+    if (f.want_rgb && lane < kPairChunks) {
+      uint8_t* out = p.obs_rgb + (size_t)e * kImgBytes + lane * 16;
+#pragma unroll
+      for (int vj = 0; vj < kView; ++vj) {
+        const uint8_t* t0p = at0 + kq0[vj];
+        const uint8_t* t1p = at1 + kq1[vj];
+#pragma unroll
+        for (int q = 0; q < kTile / 2; ++q) {   // row pair vj*4 + q: pixel rows py = 2q, 2q + 1 of tile row vj
+          const uint2 a = *reinterpret_cast<const uint2*>(t0p + q * 48);
+          const uint2 b = *reinterpret_cast<const uint2*>(t1p + q * 48);
+          st_stream_v4(out + (vj * (kTile / 2) + q) * (2 * kRowBytes), a.x, a.y, b.x, b.y);
         }
       }
     }
-    __syncwarp();  // kp is reused by this warp's next env
+    __syncwarp();  // kq is reused by this warp's next env
   }
 }
 
@@ -1022,7 +1126,9 @@ cudaError_t launch_full_obs(const EnvParams& p, uint8_t* out, int sm_count, cuda
 }
 
 // ---------------------------------------------------------------------------------------------------
-// launch helpers: persistent grids of (SMs x resident CTAs), capped by the work available
+// launch helpers: persistent grids of (SMs x resident CTAs), capped by the work available.  The resident-CTA count of
+// every kernel instance is looked up once per HANDLE (LaunchCtx::occ, one slot per instance): a process may drive
+// several handles on several devices from several threads, so nothing here is process-wide.
 template <typename Kernel>
 static cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int& blocks_per_sm) {
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1033,46 +1139,43 @@ static cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int& b
   return cudaSuccess;
 }
 
-static int current_device_slot() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return dev & 63;
-}
+// occupancy-cache slots (LaunchCtx::occ): one per kernel instance
+enum : int { kSlotGroup = 0 /* +2*log2(32/G) + STEP: 8 */, kSlotTile = 8 /* + (T==8)*4 + SWAR*2 + STEP: 8 */,
+             kSlotOrdered = 16 /* + SWAR*2 + STEP: 4 */, kSlotTma = 20 /* + STEP: 2 */, kSlotWarp = 22 /* + STEP: 2 */ };
+static_assert(kSlotWarp + 2 <= kOccSlots, "occupancy cache too small");
 
 template <int G, bool STEP>
-static cudaError_t launch_group_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_group_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_groups = (p.N + G - 1) / G;
   const size_t smem = cta_smem_bytes(G);
-  static int blocks_per_sm_dev[64] = {};  // per template instance and device; 0 = not configured yet
-  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  int& blocks_per_sm = ctx.occ[kSlotGroup + 2 * (G == 32 ? 0 : G == 16 ? 1 : G == 8 ? 2 : 3) + (STEP ? 1 : 0)];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel<G, STEP>, kThreads, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
   }
-  const int grid = min(sm_count * blocks_per_sm, (n_groups + kWarps - 1) / kWarps);
+  const int grid = min(ctx.sm_count * blocks_per_sm, (n_groups + kWarps - 1) / kWarps);
   env_kernel<G, STEP><<<grid, kThreads, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
 }
 
 template <int T, bool STEP, bool SWAR, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
-static cudaError_t launch_tile_kernel_impl(const EnvParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_tile_kernel_impl(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_smem_bytes(T);
-  static int blocks_per_sm_dev[64] = {};
-  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  int& blocks_per_sm = ctx.occ[kSlotTile + (T == 8 ? 4 : 0) + (SWAR ? 2 : 0) + (STEP ? 1 : 0)];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_tile<T, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
     if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
-  const int grid = min(sm_count * blocks_per_sm, n_tiles);
+  const int grid = min(ctx.sm_count * blocks_per_sm, n_tiles);
   env_kernel_tile<T, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_tiles);
   return cudaGetLastError();
 }
 template <int T, bool STEP>
-static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  return use_swar(p, true) ? launch_tile_kernel_impl<T, STEP, true>(p, sm_count, stream)
-                     : launch_tile_kernel_impl<T, STEP, false>(p, sm_count, stream);
+static cudaError_t launch_tile_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
+  return use_swar(p, ctx, true) ? launch_tile_kernel_impl<T, STEP, true>(p, ctx, stream)
+                                : launch_tile_kernel_impl<T, STEP, false>(p, ctx, stream);
 }
 
 #ifndef MERLIN_ORD_G
@@ -1081,25 +1184,24 @@ static cudaError_t launch_tile_kernel(const EnvParams& p, int sm_count, cudaStre
 #define MERLIN_ORD_CTAS 3
 #endif
 template <int G, bool STEP, bool SWAR, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
-static cudaError_t launch_ordered_kernel_impl(const EnvParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_ordered_kernel_impl(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int warps = THREADS / 32;
   const int n_groups = (p.N + G - 1) / G;
   const size_t smem = kAtlasBytes + warps * warp_smem_bytes(G);
-  static int blocks_per_sm_dev[64] = {};
-  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  int& blocks_per_sm = ctx.occ[kSlotOrdered + (SWAR ? 2 : 0) + (STEP ? 1 : 0)];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_ordered<G, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
     if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
-  const int grid = min(sm_count * blocks_per_sm, (n_groups + warps - 1) / warps);
+  const int grid = min(ctx.sm_count * blocks_per_sm, (n_groups + warps - 1) / warps);
   env_kernel_ordered<G, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
 }
 template <int G, bool STEP>
-static cudaError_t launch_ordered_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  return use_swar(p, true) ? launch_ordered_kernel_impl<G, STEP, true>(p, sm_count, stream)
-                     : launch_ordered_kernel_impl<G, STEP, false>(p, sm_count, stream);
+static cudaError_t launch_ordered_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
+  return use_swar(p, ctx, true) ? launch_ordered_kernel_impl<G, STEP, true>(p, ctx, stream)
+                                : launch_ordered_kernel_impl<G, STEP, false>(p, ctx, stream);
 }
 
 #ifndef MERLIN_TMA_T
@@ -1109,69 +1211,66 @@ static cudaError_t launch_ordered_kernel(const EnvParams& p, int sm_count, cudaS
 #define MERLIN_TMA_NBUF 1
 #endif
 template <int T, bool STEP, int THREADS = MERLIN_TMA_THREADS, int MINB = MERLIN_TMA_CTAS, int NBUF = MERLIN_TMA_NBUF>
-static cudaError_t launch_tile_tma_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_tile_tma_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_tma_smem_bytes(T, THREADS, NBUF);
-  static int blocks_per_sm_dev[64] = {};
-  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  int& blocks_per_sm = ctx.occ[kSlotTma + (STEP ? 1 : 0)];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
     if (MINB < blocks_per_sm) blocks_per_sm = MINB;
   }
-  const int grid = min(sm_count * blocks_per_sm, n_tiles);
+  const int grid = min(ctx.sm_count * blocks_per_sm, n_tiles);
   env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF><<<grid, THREADS, smem, stream>>>(p, n_tiles);
   return cudaGetLastError();
 }
 
 template <bool STEP>
-static cudaError_t launch_warp_kernel(const EnvParams& p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_warp_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int warps = kWarpKernelThreads / 32;
-  const size_t smem = kAtlasBytes + warps * kWarpKindStride + kChunksPerLane * 32 * 4;
-  static int blocks_per_sm_dev[64] = {};
-  int& blocks_per_sm = blocks_per_sm_dev[current_device_slot()];
+  const size_t smem = kAtlasBytes + warps * kWarpKindBytes;
+  int& blocks_per_sm = ctx.occ[kSlotWarp + (STEP ? 1 : 0)];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_warp<STEP>, kWarpKernelThreads, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
   }
-  const int grid = min(sm_count * blocks_per_sm, (p.N + warps - 1) / warps);
+  const int grid = min(ctx.sm_count * blocks_per_sm, (p.N + warps - 1) / warps);
   env_kernel_warp<STEP><<<grid, kWarpKernelThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-static int g_kernel_choice = 0;
-void set_kernel_choice(int choice) { g_kernel_choice = choice; }
-
 template <bool STEP>
-static cudaError_t launch_sized(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  int choice = g_kernel_choice;
+static cudaError_t launch_sized(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
+  const int sm_count = ctx.sm_count;
+  int choice = ctx.kernel_choice;
   if (choice == 0) {
     // symbolic-only observations are instruction-bound: the state phase alone, at high occupancy
     if (p.obs_rgb == nullptr) choice = 5;
     else choice = MERLIN_AUTO_RGB_CHOICE(p.N, sm_count);
   }
-  if (choice == 2) return launch_warp_kernel<STEP>(p, sm_count, stream);
-  if (choice == 5) return launch_sym_kernel<STEP>(p, stream);
-  if (choice == 6) return launch_ordered_kernel<MERLIN_ORD_G, STEP>(p, sm_count, stream);
+  if (choice == 2) return launch_warp_kernel<STEP>(p, ctx, stream);
+  if (choice == 5) return launch_sym_kernel<STEP>(p, ctx, stream);
+  if (choice == 6) return launch_ordered_kernel<MERLIN_ORD_G, STEP>(p, ctx, stream);
   if (choice == 4) {
-    if ((reinterpret_cast<uintptr_t>(p.obs_rgb) & 15) == 0) return launch_tile_tma_kernel<MERLIN_TMA_T, STEP>(p, sm_count, stream);
+    if ((reinterpret_cast<uintptr_t>(p.obs_rgb) & 15) == 0) return launch_tile_tma_kernel<MERLIN_TMA_T, STEP>(p, ctx, stream);
     choice = 3;  // bulk copies need a 16-byte aligned destination
   }
   if (choice == 3) {
     // tiles of 16 envs once every resident CTA gets one; smaller tiles spread a small batch over more CTAs
-    if (p.N >= sm_count * kTileCtasPerSm * 16) return launch_tile_kernel<16, STEP>(p, sm_count, stream);
-    return launch_tile_kernel<8, STEP>(p, sm_count, stream);
+    if (p.N >= sm_count * kTileCtasPerSm * 16) return launch_tile_kernel<16, STEP>(p, ctx, stream);
+    return launch_tile_kernel<8, STEP>(p, ctx, stream);
   }
   // pick the largest group size that still yields >= ~8 warps per SM; tiny batches use smaller groups
   const long long want_warps = (long long)sm_count * 8;
-  if (p.N / 32 >= want_warps) return launch_group_kernel<32, STEP>(p, sm_count, stream);
-  if (p.N / 16 >= want_warps) return launch_group_kernel<16, STEP>(p, sm_count, stream);
-  if (p.N / 8 >= want_warps) return launch_group_kernel<8, STEP>(p, sm_count, stream);
-  return launch_group_kernel<4, STEP>(p, sm_count, stream);
+  if (p.N / 32 >= want_warps) return launch_group_kernel<32, STEP>(p, ctx, stream);
+  if (p.N / 16 >= want_warps) return launch_group_kernel<16, STEP>(p, ctx, stream);
+  if (p.N / 8 >= want_warps) return launch_group_kernel<8, STEP>(p, ctx, stream);
+  return launch_group_kernel<4, STEP>(p, ctx, stream);
 }
 
-const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
-  int choice = g_kernel_choice;
+const char* step_kernel_name(int n_envs, bool rgb, const LaunchCtx& ctx) {
+  const int sm_count = ctx.sm_count;
+  int choice = ctx.kernel_choice;
   if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 5;
   if (choice == 5) return "merlin::env_kernel_sym<true>";
   if (choice == 2) return "merlin::env_kernel_warp<true>";
@@ -1186,11 +1285,11 @@ const char* step_kernel_name(int n_envs, bool rgb, int sm_count) {
   return "merlin::env_kernel<4,true>";
 }
 
-cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  return launch_sized<true>(p, sm_count, stream);
+cudaError_t launch_env_step(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
+  return launch_sized<true>(p, ctx, stream);
 }
-cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream) {
-  return launch_sized<false>(p, sm_count, stream);
+cudaError_t launch_env_reset(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
+  return launch_sized<false>(p, ctx, stream);
 }
 
 }  // namespace merlin

@@ -26,6 +26,7 @@ __host__ __device__ constexpr int cta_smem_bytes(int G) { return kAtlasBytes + k
 struct EnvParams {
   // geometry / behaviour
   int N, W, H, max_steps, cell_stride, n_layouts, vis_words, stuck_max_stay;
+  int cursor_stride;           // a restarting env moves on by this many pool slots: N mod L, or 1 when L divides N
   uint32_t flags;
   double stuck_penalty, explore_bonus;
   // handle-owned device state
@@ -52,18 +53,43 @@ struct EnvParams {
   int32_t* out_ep_length;
   uint8_t* out_stuck;
   float* out_done;
+  // policy I/O (merlin_env_policy_step): `logits` != nullptr replaces `actions` -- the action of env e is sampled in the
+  // kernel from logits[e][0..n_actions) (or is their argmax when `greedy`) and stored with its log-probability
+  const float* logits;         // [N][n_actions]
+  const float* value_in;       // [N] or nullptr
+  int64_t* out_action;         // [N]
+  float* out_logp;             // [N]
+  float* out_value;            // [N] or nullptr: copy of value_in (row t of a rollout's value tensor)
+  uint32_t* draws;             // [N] handle-owned: how many actions env e has drawn (the Philox counter)
+  uint32_t seed_lo, seed_hi;   // sampler key
+  int greedy;
+  int logits_stride, value_stride;   // in floats; rows of `logits` / elements of `value_in`
+  // first-episode record (deterministic evaluation, "freeze after done"): when env e finishes an episode and
+  // rec_finished[e] == 0, its return / length / terminated flag are stored and rec_finished[e] becomes 1
+  uint8_t* rec_finished;       // [N] in/out, or nullptr
+  float* rec_return;           // [N]
+  int32_t* rec_length;         // [N]
+  uint8_t* rec_goal;           // [N] 1 = the episode ended by termination with a positive reward (goal reached)
+};
+
+// Per-handle launch context: kernel choice, observation path and the occupancy cache live in the handle (a process may
+// hold several handles on several devices, driven from different threads).
+constexpr int kOccSlots = 32;
+struct LaunchCtx {
+  int sm_count;
+  int kernel_choice;      // 0 = automatic, 1..6 as merlin_set_kernel_choice
+  int observation_path;   // 0 = automatic, 1 = per-cell, 2 = row-parallel wherever built
+  int* occ;               // [kOccSlots] resident CTAs per SM per kernel instance, 0 = not configured yet
 };
 
 // kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile,
 // 4 = env_kernel_tile_tma (tile kernel, frames through cp.async.bulk), 5 = env_kernel_sym (state phase only: any RGB
 // output pointer is ignored), 6 = env_kernel_ordered (group kernel, groups handed out in order)
-void set_kernel_choice(int choice);
 // observation path: 0 = automatic (row-parallel obs_swar.cuh in the symbolic-only kernel when W >= 7), 1 = per-cell
 // everywhere, 2 = row-parallel in every kernel that has it (symbolic-only, tile, ordered)
-void set_observation_path(int path);
-const char* step_kernel_name(int n_envs, bool rgb, int sm_count);
-cudaError_t launch_env_step(const EnvParams& p, int sm_count, cudaStream_t stream);
-cudaError_t launch_env_reset(const EnvParams& p, int sm_count, cudaStream_t stream);
+const char* step_kernel_name(int n_envs, bool rgb, const LaunchCtx& ctx);
+cudaError_t launch_env_step(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream);
+cudaError_t launch_env_reset(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream);
 // Frames from stored symbolic observations (RGBImgPartialObsWrapper.observation as a batch op, with an optional
 // row gather): out[m] = frame(sym[index ? index[m] : m]).  blocked = false: u8[M][56][56][3] as the env kernel writes
 // them; blocked = true: u8[M][14][14][48], every 4x4 pixel block contiguous with channel index c*16 + dy*4 + dx (the

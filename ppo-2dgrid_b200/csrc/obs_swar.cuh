@@ -123,26 +123,19 @@ MERLIN_HD uint64_t visibility8(uint64_t transp) {
   uint32_t seed = 1u << (kView / 2);
 #pragma unroll
   for (int vj = kView - 1; vj >= 0; --vj) {
-    const uint32_t T = (uint32_t)(transp >> (8 * vj)) & 0x7f;
-    uint32_t v = seed;
-    const uint32_t TL = T & 0x3f;
-#pragma unroll
-    for (int k = 0; k < kView - 1; ++k) v |= (v & TL) << 1;
-    const uint32_t A = v & TL;
-    const uint32_t TR = T & 0x7e;
-#pragma unroll
-    for (int k = 0; k < kView - 1; ++k) v |= (v & TR) >> 1;
-    const uint32_t B = v & TR;
+    uint32_t v;
+    seed = vis_row(seed, (uint32_t)(transp >> (8 * vj)) & 0x7f, v);   // env_logic.cuh: carry-chain form of a row
     vis |= (uint64_t)v << (8 * vj);
-    seed = (A | (A << 1) | B | (B >> 1)) & 0x7f;
   }
   return vis;
 }
 
 // What the agent sees.  g[vi]: byte vj = packed code at view (vi, vj) AFTER the invisible cells were erased (0) and the
 // agent's own cell (3, 6) was replaced by what it carries (or empty); seen[vi]: 0xff in byte vj where visible.
+// `doors` = false promises that no cell of the grid is a closed / locked door (walls are then the only opaque cells):
+// one byte-parallel type test per group instead of three.
 MERLIN_HD void observe_swar(const EnvState& s, const uint8_t* grid, int W, int H, uint64_t (&g)[kView],
-                            uint64_t (&seen)[kView]) {
+                            uint64_t (&seen)[kView], bool doors = true) {
   // window origin: get_view_exts
   const int x0 = s.dir == 0 ? s.x : (s.dir == 2 ? s.x - (kView - 1) : s.x - kView / 2);
   const int y0 = s.dir == 1 ? s.y : (s.dir == 3 ? s.y - (kView - 1) : s.y - kView / 2);
@@ -167,7 +160,8 @@ MERLIN_HD void observe_swar(const EnvState& s, const uint8_t* grid, int W, int H
 #pragma unroll
   for (int vi = 0; vi < kView; ++vi) {
     const uint64_t t4 = g[vi] & (kB01 * 0x0f);
-    const uint64_t tb = nibble_ne(t4, T_WALL) & nibble_ne(t4, T_DOOR_CLOSED) & nibble_ne(t4, T_DOOR_LOCKED) & kLow7;
+    uint64_t tb = nibble_ne(t4, T_WALL) & kLow7;
+    if (doors) tb &= nibble_ne(t4, T_DOOR_CLOSED) & nibble_ne(t4, T_DOOR_LOCKED);
     // gather the seven byte LSBs into bits 0..6
     const uint64_t bits = (tb * 0x0102040810204080ull) >> 56;
     tm |= bits << (8 * vi);
@@ -199,13 +193,17 @@ MERLIN_HD uint32_t perm(uint32_t a, uint32_t b, uint32_t sel) {
 
 // The 21-byte piece of the symbolic image for group vi (cells vj = 0..6, three bytes each) as six little-endian words
 // (the last one holds a single byte): Grid.encode's (type, colour, state) of the visible codes, zeros where unseen.
-MERLIN_HD void encode_group(uint64_t codes, uint32_t (&w)[6]) {
+// `doors` = false promises that no code is a closed / locked door: type = the low nibble, state = 0.
+MERLIN_HD void encode_group(uint64_t codes, uint32_t (&w)[6], bool doors = true) {
   const uint64_t t4 = codes & (kB01 * 0x0f);
   const uint64_t col = (codes >> 4) & (kB01 * 0x07);
-  const uint64_t door_lsb = ((t4 + kB01 * 0x05) >> 4) & kB01;          // low nibble >= 11: closed / locked door
-  const uint64_t door = (door_lsb << 8) - door_lsb;
-  const uint64_t typ = (t4 & ~door) | (kB01 * T_DOOR_OPEN & door);      // doors encode as type 4 ...
-  const uint64_t st = (((t4 | kB01 * 0x10) - kB01 * 0x0a) & (kB01 * 0x03)) & door;  // ... with state 1 / 2
+  uint64_t typ = t4, st = 0;
+  if (doors) {
+    const uint64_t door_lsb = ((t4 + kB01 * 0x05) >> 4) & kB01;          // low nibble >= 11: closed / locked door
+    const uint64_t door = (door_lsb << 8) - door_lsb;
+    typ = (t4 & ~door) | (kB01 * T_DOOR_OPEN & door);                    // doors encode as type 4 ...
+    st = (((t4 | kB01 * 0x10) - kB01 * 0x0a) & (kB01 * 0x03)) & door;    // ... with state 1 / 2
+  }
   const uint32_t t0 = (uint32_t)typ, t1 = (uint32_t)(typ >> 32), c0 = (uint32_t)col, c1 = (uint32_t)(col >> 32);
   const uint32_t s0 = (uint32_t)st, s1 = (uint32_t)(st >> 32);
   // byte p = 3 vj + k of the piece; words: T0 C0 S0 T1 | C1 S1 T2 C2 | S2 T3 C3 S3 | T4 C4 S4 T5 | C5 S5 T6 C6 | S6

@@ -22,6 +22,8 @@ EXPORTS = (
     "merlin_env_state_ptrs", "merlin_env_read_state", "merlin_env_bad_actions", "merlin_env_launch_count",
     "merlin_set_kernel_choice", "merlin_set_observation_path", "merlin_env_step_kernel", "merlin_env_render", "merlin_env_render_f32", "merlin_env_full_obs", "merlin_gae",
     "merlin_pack_cell", "merlin_last_error", "merlin_version",
+    "merlin_env_policy_step", "merlin_env_seed_sampler", "merlin_env_rearm", "merlin_env_set_kernel_choice",
+    "merlin_env_set_observation_path", "merlin_env_write_state",
 )
 
 
@@ -36,6 +38,14 @@ class EnvConfig(C.Structure):
 class StepExtras(C.Structure):
     _fields_ = [("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stuck", C.c_void_p),
                 ("done", C.c_void_p)]
+
+
+class PolicyIO(C.Structure):
+    """merlin_policy_io_t: device pointers of one fused act -> sample -> step -> store transition."""
+    _fields_ = [("logits", C.c_void_p), ("value", C.c_void_p), ("action", C.c_void_p), ("logprob", C.c_void_p),
+                ("value_out", C.c_void_p), ("greedy", C.c_int32), ("logits_stride", C.c_int32),
+                ("value_stride", C.c_int32), ("finished", C.c_void_p),
+                ("first_return", C.c_void_p), ("first_length", C.c_void_p), ("first_goal", C.c_void_p)]
 
 
 _lib = None
@@ -63,8 +73,15 @@ def load():
     lib.merlin_env_set_cursors.argtypes = [vp, vp]
     lib.merlin_env_reset.argtypes = [vp, vp, vp, vp, vp]
     lib.merlin_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(StepExtras), vp]
+    lib.merlin_env_policy_step.argtypes = [vp, C.POINTER(PolicyIO), vp, vp, vp, vp, vp, C.POINTER(StepExtras), vp]
+    lib.merlin_env_seed_sampler.argtypes = [vp, C.c_uint64]
+    lib.merlin_env_rearm.argtypes = [vp, vp]
+    lib.merlin_env_set_kernel_choice.argtypes = [vp, C.c_int]
+    lib.merlin_env_set_observation_path.argtypes = [vp, C.c_int]
     lib.merlin_env_state_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     lib.merlin_env_read_state.argtypes = [vp, vp, vp, vp]
+    lib.merlin_env_write_state.argtypes = [vp, vp, vp, vp]
+    lib.merlin_env_write_state.restype = C.c_int
     lib.merlin_env_bad_actions.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.merlin_env_launch_count.argtypes = [vp]
     lib.merlin_env_launch_count.restype = i64
@@ -88,7 +105,9 @@ def load():
     for name in ("merlin_env_create", "merlin_env_destroy", "merlin_env_upload_layouts", "merlin_env_set_tile_atlas",
                  "merlin_env_generate_layouts", "merlin_env_read_layouts", "merlin_env_layout_count",
                  "merlin_env_set_cursors", "merlin_env_reset", "merlin_env_step", "merlin_env_state_ptrs",
-                 "merlin_env_read_state", "merlin_env_bad_actions", "merlin_gae"):
+                 "merlin_env_read_state", "merlin_env_bad_actions", "merlin_gae", "merlin_env_policy_step",
+                 "merlin_env_seed_sampler", "merlin_env_rearm", "merlin_env_set_kernel_choice",
+                 "merlin_env_set_observation_path"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     if os.environ.get("MERLIN_OBSERVATION_PATH"):
@@ -100,7 +119,8 @@ def load():
 
 def set_kernel_choice(choice):
     """0 = automatic, 1 = group kernel, 2 = warp-per-env kernel, 3 = CTA-tile kernel, 4 = CTA-tile kernel with TMA frame
-    stores, 5 = symbolic-only kernel, 6 = group kernel with in-order hand-out (process-wide; identical results)."""
+    stores, 5 = symbolic-only kernel, 6 = group kernel with in-order hand-out.  Process-wide DEFAULT for envs without a
+    setting of their own (`BatchedMerlinEnv.set_kernel_choice`); identical results."""
     check(load().merlin_set_kernel_choice(int(choice)))
 
 

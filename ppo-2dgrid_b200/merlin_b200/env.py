@@ -48,6 +48,11 @@ class StepBuffers:
                                        self.stuck.data_ptr(), self.done.data_ptr())
 
 
+class _PolicyIO:
+    """Tensors + the C struct of one fused policy transition (BatchedMerlinEnv.make_policy_io)."""
+    __slots__ = ("logits", "value", "action", "logprob", "value_out", "record", "_c")
+
+
 class BatchedMerlinEnv:
     def __init__(self, num_envs, cells=None, agent=None, *, enc=None, width=None, height=None, max_steps=None,
                  device="cuda", n_actions=3, auto_reset=True, reset_mode="next", stuck_penalty=False,
@@ -55,7 +60,7 @@ class BatchedMerlinEnv:
                  want_rgb=True, generate=None, episode_stats=True):
         """cells: packed u8[L, H*W] (merlin_b200.codes) or `enc`: Grid.encode() arrays u8[L, W, H, 3];
         agent: i32[L, 3] = (x, y, dir).  `reset_mode`: "next" advances each env's pool cursor by num_envs at
-        every restart (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
+        every restart, modulo the pool size (by one slot when the pool size divides num_envs) (PPO: a fresh layout per episode), "same" replays the same layout (FOMAML task)."""
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("BatchedMerlinEnv needs a CUDA device (no CPU fallback)")
@@ -79,6 +84,10 @@ class BatchedMerlinEnv:
             if width is None:
                 width = height = int(round(cells.shape[1] ** 0.5))
         self.num_envs, self.width, self.height = int(num_envs), int(width), int(height)
+        # what evaluators need to rebuild this env's layouts for other seeds: the layout routine (known when the pool was
+        # generated here or the env came from ScenarioCreator.create_batched_env, else None) and the grid size
+        self.difficulty = generate[0] if generate is not None else None
+        self.size = self.width
         self.n_actions = n_actions
         self.want_symbolic, self.want_rgb = want_symbolic, want_rgb
         # episode_stats=False: step() skips the optional per-env outputs (episode return / length, stuck, done): the
@@ -218,6 +227,87 @@ class BatchedMerlinEnv:
                 "done": b.done, "obs_symbolic": sym}
         return obs, b.reward, b.terminated, b.truncated, info
 
+    # ---- fused policy transition ------------------------------------------------------------------
+    def seed_sampler(self, seed):
+        """Key of the in-kernel action sampler (Philox4x32-10); resets every env's draw counter.  Synchronous."""
+        _lib.check(self._lib.merlin_env_seed_sampler(self._h, int(seed) & (2**64 - 1)))
+        self._sampler_seeded = True
+
+    def make_policy_io(self, logits, value=None, action=None, logprob=None, value_out=None, greedy=False, record=None):
+        """Bind the tensors of one fused transition once (pointers are baked in; reuse the object every step or
+        capture it in a CUDA graph).  `logits` f32[N, A], `value` f32[N]; outputs `action` i64[N], `logprob` f32[N],
+        `value_out` f32[N] may be rows of rollout tensors (allocated here when None).  `record`: dict with tensors
+        finished (bool/u8), first_return (f32), first_length (i32), first_goal (bool/u8), all [N]: first-episode record."""
+        N, dev = self.num_envs, self.device
+
+        def need(t, dtype, shape, name):
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=dev)
+            ok_dtype = t.dtype == dtype or (dtype == torch.uint8 and t.dtype == torch.bool)
+            if tuple(t.shape) != tuple(shape) or not ok_dtype or not t.is_contiguous() or t.device != dev:
+                raise ValueError(f"{name} must be a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+            return t
+
+        def strided(t, cols, name):
+            # [N, cols] (or [N]) float32 with unit inner stride and any row stride: a slice of a fused output matrix
+            shape = (N, cols) if cols else (N,)
+            if (t.dtype != torch.float32 or tuple(t.shape) != shape or t.device != dev
+                    or (cols > 1 and t.stride(1) != 1) or (N > 1 and t.stride(0) < max(cols, 1))):
+                raise ValueError(f"{name} must be float32 of shape {shape} on {dev} with unit inner stride")
+            return t, int(t.stride(0))
+
+        io = _PolicyIO()
+        io.logits, ls = strided(logits, self.n_actions, "logits")
+        io.value, vs = (None, 0) if value is None else strided(value, 0, "value")
+        io.action = need(action, torch.int64, (N,), "action")
+        io.logprob = need(logprob, torch.float32, (N,), "logprob")
+        io.value_out = None if (value is None) else need(value_out, torch.float32, (N,), "value_out")
+        io.record = None
+        c = _lib.PolicyIO(io.logits.data_ptr(), io.value.data_ptr() if io.value is not None else None,
+                          io.action.data_ptr(), io.logprob.data_ptr(),
+                          io.value_out.data_ptr() if io.value_out is not None else None, 1 if greedy else 0, ls, vs,
+                          None, None, None, None)
+        if record is not None:
+            io.record = {"finished": need(record["finished"], torch.uint8, (N,), "finished"),
+                         "first_return": need(record["first_return"], torch.float32, (N,), "first_return"),
+                         "first_length": need(record["first_length"], torch.int32, (N,), "first_length"),
+                         "first_goal": need(record["first_goal"], torch.uint8, (N,), "first_goal")}
+            c.finished, c.first_return = io.record["finished"].data_ptr(), io.record["first_return"].data_ptr()
+            c.first_length, c.first_goal = io.record["first_length"].data_ptr(), io.record["first_goal"].data_ptr()
+        io._c = c
+        return io
+
+    def policy_step(self, io, out_obs=None, out_symbolic=None, out=None, frames=True):
+        """One rollout transition in ONE launch: sample an action per env from `io.logits` (or argmax), store action /
+        log-probability / value into `io`'s tensors, step every env and write the next observation.  Returns the same
+        5-tuple as `step`; the action taken is `io.action`.  Replaces Categorical(logits).sample() + log_prob + env.step +
+        the rollout stores of src/ppo.py:70-86 and src/fomaml.py:65-84."""
+        if not getattr(self, "_sampler_seeded", False):
+            # follow torch's seeding (torch.manual_seed) so that runs are reproducible and ranks differ
+            self.seed_sampler(int(torch.randint(0, 2**62, (1,)).item()))
+        obs = (out_obs if out_obs is not None else self.obs) if frames else None
+        sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
+        b = out if out is not None else self
+        _lib.check(self._lib.merlin_env_policy_step(
+            self._h, C.byref(io._c), obs.data_ptr() if obs is not None else None,
+            sym.data_ptr() if sym is not None else None, b.reward.data_ptr(), b.terminated.data_ptr(),
+            b.truncated.data_ptr(), C.byref(b._extras) if self.episode_stats else None, self._stream()))
+        info = {"episode_return": b.episode_return, "episode_length": b.episode_length, "stuck": b.stuck,
+                "done": b.done, "obs_symbolic": sym}
+        return obs, b.reward, b.terminated, b.truncated, info
+
+    def set_kernel_choice(self, choice):
+        """This env's step-kernel mapping (0 automatic .. 6, see merlin_b200.set_kernel_choice); -1 = follow the
+        process-wide default again."""
+        _lib.check(self._lib.merlin_env_set_kernel_choice(self._h, int(choice)))
+
+    def set_observation_path(self, path):
+        _lib.check(self._lib.merlin_env_set_observation_path(self._h, int(path)))
+
+    def rearm(self):
+        """Clear the in-kernel work-ticket counters (after an application-level recovery from a device fault)."""
+        _lib.check(self._lib.merlin_env_rearm(self._h, self._stream()))
+
     def full_observation(self, out=None):
         """FullyObsWrapper's observation of every env's current state: u8[N, W, H, 3] (`Grid.encode()` indexed [x][y],
         the agent's cell = (10, 0, agent_dir))."""
@@ -285,6 +375,32 @@ class BatchedMerlinEnv:
                 "dir": ((pose >> 16) & 3).astype(np.int32), "carry": ((pose >> 24) & 0x7F).astype(np.int32),
                 "step_count": a[:, 1].copy(), "layout": a[:, 2].copy(), "stay": (stuck & 0xFFFF).astype(np.int32),
                 "episode_return": epr}
+
+    def state_raw(self):
+        """Host copy of the packed state exactly as the device holds it: (i32[N, 4], episode_return f32[N]) -- what
+        `load_state_raw` takes back (save / resume a rollout state)."""
+        a = np.empty((self.num_envs, 4), dtype=np.int32)
+        epr = np.empty(self.num_envs, dtype=np.float32)
+        _lib.check(self._lib.merlin_env_read_state(self._h, a.ctypes.data, None, epr.ctypes.data))
+        return a, epr
+
+    def load_state_raw(self, state, episode_return=None, cells=None):
+        """Overwrite the env state (synchronous, validated): `state` i32[N, 4] as `state_raw` returns it; column 1 is
+        the episode clock `step_count`."""
+        st = np.ascontiguousarray(state, dtype=np.int32)
+        if st.shape != (self.num_envs, 4):
+            raise ValueError("state must be int32[num_envs, 4]")
+        epr = None if episode_return is None else np.ascontiguousarray(episode_return, dtype=np.float32)
+        cl = None if cells is None else np.ascontiguousarray(cells, dtype=np.uint8)
+        _lib.check(self._lib.merlin_env_write_state(self._h, st.ctypes.data, cl.ctypes.data if cl is not None else None,
+                                                    epr.ctypes.data if epr is not None else None))
+
+    def stagger_episode_clocks(self, seed=0):
+        """Give every env a random episode clock in [0, max_steps): a batch that was reset together then truncates at
+        the steady-state rate (N / max_steps envs per step) instead of all at once (benchmarks)."""
+        st, epr = self.state_raw()
+        st[:, 1] = np.random.default_rng(seed).integers(0, self.max_steps, self.num_envs, dtype=np.int32)
+        self.load_state_raw(st, epr)
 
     def pose_numpy(self):
         s = self.state_numpy()

@@ -19,59 +19,71 @@ from merlin_b200 import layouts as _layouts
 
 @torch.no_grad()
 def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=None, deterministic=True, poll=64,
-                   env=None, act_fn=None, use_cuda_graph=True):
+                   env=None, act_fn=None, use_cuda_graph=True, params=None):
     """Returns (returns f64[len(seeds)], lengths i64[len(seeds)], reached_goal bool[len(seeds)]).
-    `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` replaces `policy.act` (e.g. per-task adapted weights).
-    A CNN policy acting by itself is evaluated in chunks of `poll` steps replayed from one CUDA graph (policy input
-    rendering, forward, argmax, env step, first-episode bookkeeping: no host work inside a chunk)."""
-    from .actor_critic import CNNActorCritic
+    A CNN policy is evaluated on the lean path: per step the policy's float32 input is rendered from the env's
+    147-byte symbolic image, the two trunks run as one fused network (`RolloutPolicy`; `params` = stacked per-task
+    weights evaluates task b under its own weights) and ONE launch takes the argmax, steps every env and keeps the
+    first-episode record (`BatchedMerlinEnv.policy_step(greedy, record)`); chunks of `poll` steps are replayed from
+    one CUDA graph, no host work inside a chunk.  `act_fn(obs u8[B,56,56,3]) -> actions i64[B]` selects the generic
+    path instead (frames + torch-side bookkeeping)."""
+    from .actor_critic import CNNActorCritic, RolloutPolicy
     seeds = [int(s) for s in seeds]
     B = len(seeds)
     cells, agent = _layouts.generate(difficulty, size, seeds)
-    # a CNN policy acting by itself needs no u8 frames at all: the step kernel writes the 147-byte symbolic image only and
-    # the policy's float32 first-layer input is rendered from it (two launches instead of a frame + three cast/layout passes)
     lean = act_fn is None and isinstance(policy, CNNActorCritic) and policy.blocked_first_layer
     if env is None or env.num_envs != B:
         env = BatchedMerlinEnv(B, cells, agent, width=size, height=size, max_steps=max_steps, device=device,
-                               reset_mode="same", want_symbolic=lean)
+                               reset_mode="same", want_symbolic=lean, want_rgb=not lean)
     else:
         env.upload_layouts(cells, agent)
         lean = lean and env.obs_symbolic is not None
+    if params is not None and not lean:
+        raise ValueError("per-task weights are evaluated on the lean CNN path only")
     env.set_cursors(np.arange(B, dtype=np.int32))
     dev = env.device
-    ret = torch.zeros(B, dtype=torch.float32, device=dev)
-    length = torch.zeros(B, dtype=torch.int32, device=dev)
-    goal = torch.zeros(B, dtype=torch.bool, device=dev)
-    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    rec = {"finished": torch.zeros(B, dtype=torch.bool, device=dev), "first_return": torch.zeros(B, dtype=torch.float32, device=dev),
+           "first_length": torch.zeros(B, dtype=torch.int32, device=dev), "first_goal": torch.zeros(B, dtype=torch.bool, device=dev)}
+    finished = rec["finished"]
     obs, _ = env.reset(frames=not lean)
     was_training = policy.training
     policy.eval()
-    if lean:
-        weights = policy.blocked_weights()
-        policy_in = torch.empty((B, 14, 14, 48), dtype=torch.float32, device=dev)
 
-        def act_fn(_):
-            x = env.render(env.obs_symbolic, out=policy_in, blocked=True, dtype=torch.float32)
-            return policy.act(x, deterministic=deterministic, blocked=weights)[0]
-    elif act_fn is None:
-        def act_fn(o):
-            return policy.act(o, deterministic=deterministic)[0]
+    if act_fn is not None:  # generic path: caller-chosen actions, bookkeeping in torch
+        ret, length, goal = rec["first_return"], rec["first_length"], rec["first_goal"]
 
-    def advance(obs):
-        action = act_fn(obs)
-        obs, _, term, _, info = env.step(action, frames=not lean)
-        first = (info["episode_length"] > 0) & ~finished
-        ret.copy_(torch.where(first, info["episode_return"], ret))
-        length.copy_(torch.where(first, info["episode_length"], length))
-        goal.logical_or_(first & term)
-        finished.logical_or_(first)
-        return obs
+        def advance(obs):
+            obs, _, term, _, info = env.step(act_fn(obs))
+            first = (info["episode_length"] > 0) & ~finished
+            ret.copy_(torch.where(first, info["episode_return"], ret))
+            length.copy_(torch.where(first, info["episode_length"], length))
+            goal.logical_or_(first & term)
+            finished.logical_or_(first)
+            return obs
+    else:
+        A = env.n_actions
+        if lean:
+            rp = RolloutPolicy(policy, params=params)
+            heads = torch.zeros((2 * B, 1, A) if params is not None else (2, B, A), dtype=torch.float32, device=dev)
+            hv = heads.view(B, 2, A) if params is not None else None
+            logits, value = (hv[:, 0], hv[:, 1, 0]) if params is not None else (heads[0], heads[1, :, 0])
+            policy_in = torch.empty((B, 14, 14, 48), dtype=torch.float32, device=dev)
+        else:
+            logits = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        io = env.make_policy_io(logits, greedy=deterministic, record=rec)
+
+        def advance(obs):
+            if lean:
+                rp(env.render(env.obs_symbolic, out=policy_in, blocked=True, dtype=torch.float32), out=heads)
+            else:
+                logits.copy_(policy(obs if isinstance(policy, CNNActorCritic) else obs.reshape(B, -1))[0])
+            return env.policy_step(io, frames=not lean)[0]
 
     if lean and use_cuda_graph and dev.type == "cuda":
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator); acts, does not step
-            act_fn(None)
+        with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator); evaluates, does not step
+            rp(policy_in.zero_(), out=heads)
         torch.cuda.current_stream(dev).wait_stream(side)
         chunk = torch.cuda.CUDAGraph()
         with torch.cuda.graph(chunk):
@@ -88,7 +100,17 @@ def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=Non
             if (t + 1) % poll == 0 and bool(finished.all()):
                 break
     policy.train(was_training)
-    return ret.double().cpu().numpy(), length.long().cpu().numpy(), goal.cpu().numpy()
+    return (rec["first_return"].double().cpu().numpy(), rec["first_length"].long().cpu().numpy(),
+            rec["first_goal"].cpu().numpy())
+
+
+def scenario_geometry(sc, difficulty):
+    """(layout-routine name, grid size, max_steps or None) of a scenario-table entry, merged with the YAML's global
+    section exactly as `ScenarioCreator.create_env` / `create_batched_env` merge it."""
+    from src.custom_envs.register import DIFFICULTY_OF
+    entry = sc._difficulty_cfg(difficulty)
+    params = sc._env_params(entry)
+    return DIFFICULTY_OF[entry["env_id"]], int(params.get("size", 16)), params.get("max_steps")
 
 
 def evaluate_policy(agent, env_or_creator, episodes=3, seed=None, difficulty=None):
@@ -96,26 +118,30 @@ def evaluate_policy(agent, env_or_creator, episodes=3, seed=None, difficulty=Non
     ScenarioCreator (then `difficulty` names the scenario), a BatchedMerlinEnv, or a reference-style single env."""
     base = seed if seed is not None else 0
     seeds = [base + ep for ep in range(episodes)]
+    max_steps = None
     if hasattr(env_or_creator, "create_batched_env"):
-        sc = env_or_creator
-        from src.custom_envs.register import DIFFICULTY_OF
-        diff = DIFFICULTY_OF[sc.get_env_id(difficulty)]
-        size = int(sc.config["difficulties"][difficulty].get("params", {}).get("size", 16))
+        diff, size, max_steps = scenario_geometry(env_or_creator, difficulty)
     elif isinstance(env_or_creator, BatchedMerlinEnv):
-        diff, size = env_or_creator.difficulty, env_or_creator.size
+        env = env_or_creator
+        diff = env.difficulty or difficulty
+        if diff is None:
+            raise ValueError("this BatchedMerlinEnv does not know its layout routine: pass difficulty=... "
+                             "(envs made by ScenarioCreator.create_batched_env carry it)")
+        if env.width != env.height:
+            raise ValueError("evaluation layouts are generated for square grids")
+        size, max_steps = env.width, env.max_steps
     else:
         u = env_or_creator.unwrapped
-        diff, size = u.difficulty, u.size
-    r, n, _ = evaluate_seeds(agent.ac, diff, size, seeds, device=agent.device if agent.device.type == "cuda" else "cuda")
+        diff, size, max_steps = u.difficulty, u.size, getattr(u, "max_steps", None)
+    r, n, _ = evaluate_seeds(agent.ac, diff, size, seeds, max_steps=max_steps,
+                             device=agent.device if agent.device.type == "cuda" else "cuda")
     return r.tolist(), n.tolist()
 
 
 def evaluate_model(sc, policy, difficulty, seeds, device="cuda"):
     """src/sweep_checkpoints.py:58-78 -- (mean reward, mean steps) over `seeds`."""
-    from src.custom_envs.register import DIFFICULTY_OF
-    diff = DIFFICULTY_OF[sc.get_env_id(difficulty)]
-    size = int(sc.config["difficulties"][difficulty].get("params", {}).get("size", 16))
-    r, n, _ = evaluate_seeds(policy, diff, size, seeds, device=device)
+    diff, size, max_steps = scenario_geometry(sc, difficulty)
+    r, n, _ = evaluate_seeds(policy, diff, size, seeds, device=device, max_steps=max_steps)
     return float(np.mean(r)), float(np.mean(n))
 
 

@@ -24,7 +24,7 @@ from merlin_b200 import BatchedMerlinEnv, gae as gae_kernel
 from merlin_b200 import layouts as _layouts
 
 from . import parallel
-from .actor_critic import CNNActorCritic, MLPActorCritic
+from .actor_critic import CNNActorCritic, MLPActorCritic, RolloutPolicy
 
 
 class FOMAML:
@@ -32,6 +32,10 @@ class FOMAML:
         self.sc = scenario_creator
         self.difficulty = difficulty
         self.device = torch.device(device)
+        if self.device.type != "cuda" and torch.cuda.is_available():
+            # the reference's default is device="cpu"; here meta_train_step / few_shot_evaluate run task-batched on the
+            # GPU (there is no CPU env), so the policies live where the env kernels write: the current CUDA device
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lr_inner = lr_inner
 
         cfg = self.sc.config["difficulties"].get(difficulty)
@@ -78,7 +82,7 @@ class FOMAML:
         if env is None:
             dev = self.device if self.device.type == "cuda" else "cuda"
             env = BatchedMerlinEnv(B, cells, agent, width=self.size, height=self.size, device=dev, reset_mode="same",
-                                   want_symbolic=False)
+                                   want_symbolic=True)
             self._envs[B] = env
         else:
             env.upload_layouts(cells, agent)
@@ -95,58 +99,102 @@ class FOMAML:
         """`steps` transitions from a fresh reset.  `env`: a BatchedMerlinEnv whose B envs are B tasks (`policy`
         acts for all of them; `params` = stacked per-task weights evaluates task b with its own weights), or a
         reference-style single env (then `task_seed` re-seeds every reset, as in the reference).
-        Returns the reference's dict; batched tensors are time-major `[steps, B, ...]`."""
+        Returns the reference's dict; batched tensors are time-major `[steps, B, ...]` (`obs` is rendered lazily from
+        the stored symbolic observations the first time it is read)."""
         if not isinstance(env, BatchedMerlinEnv):
             return self._collect_single(env, policy, steps, task_seed)
         if self.use_cuda_graph and policy is self.meta_policy:
             return self._collect_graphed(env, steps, params)
         buf = self._rollout_buffers(env, steps)
         self._rollout_body(env, policy, params, steps, buf)
-        return self._rollout_result(buf, steps)
+        return self._rollout_result(env, buf, steps)
+
+    def _lean(self, env, policy):
+        """The fused rollout path: CNN policy on the env's own symbolic observations (no u8 frame is ever written)."""
+        return self.use_cnn and getattr(policy, "blocked_first_layer", False) and env.obs_symbolic is not None
 
     def _rollout_buffers(self, env, steps):
         B, dev = env.num_envs, env.device
         f32 = dict(dtype=torch.float32, device=dev)
-        buf = {"obs": torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev),
-               "act": torch.empty((steps, B), dtype=torch.long, device=dev), "rew": torch.empty((steps, B), **f32),
+        lean = self._lean(env, self.meta_policy)
+        buf = {"act": torch.empty((steps, B), dtype=torch.long, device=dev), "rew": torch.empty((steps, B), **f32),
                "val": torch.empty((steps, B), **f32), "logp": torch.empty((steps, B), **f32),
                "done": torch.empty((steps, B), **f32), "ep_ret": torch.empty((steps, B), **f32),
-               "ep_len": torch.empty((steps, B), dtype=torch.int32, device=dev), "last_val": torch.empty(B, **f32)}
-        # the step kernel writes reward / done / episode statistics of step t straight into row t
+               "ep_len": torch.empty((steps, B), dtype=torch.int32, device=dev), "last_val": torch.empty(B, **f32),
+               "heads": torch.zeros((2 * B, 1, 3), **f32)}
+        if lean:
+            buf["sym"] = torch.empty((steps + 1, B, 7, 7, 3), dtype=torch.uint8, device=dev)
+            buf["policy_in"] = torch.empty((B, 14, 14, 48), **f32)
+        else:
+            buf["obs"] = torch.empty((steps + 1, B, 56, 56, 3), dtype=torch.uint8, device=dev)
+        # the step kernel writes reward / done / episode statistics of step t straight into row t, and -- fused policy
+        # transition -- the sampled action, its log-probability and the value as well
         scratch = {k: torch.empty(B, dtype=torch.bool, device=dev) for k in ("terminated", "truncated", "stuck")}
         buf["rows"] = [env.make_step_buffers(reward=buf["rew"][t], done=buf["done"][t], episode_return=buf["ep_ret"][t],
                                              episode_length=buf["ep_len"][t], **scratch) for t in range(steps)]
         return buf
 
+    def _policy_ios(self, env, buf, steps, logits, value):
+        return [env.make_policy_io(logits, value, action=buf["act"][t], logprob=buf["logp"][t], value_out=buf["val"][t])
+                for t in range(steps)]
+
     def _rollout_body(self, env, policy, params, steps, buf):
+        B = env.num_envs
+        lean = "sym" in buf
+        if lean:
+            # the weights do not change during the rollout: both trunks (of every task) packed once into one fused network
+            rp = RolloutPolicy(policy, params=params)
+            heads = buf["heads"] if params is not None else buf["heads"].view(2, B, 3)
+            hv = heads.view(B, 2, 3) if params is not None else None
+            logits, value = (hv[:, 0], hv[:, 1, 0]) if params is not None else (heads[0], heads[1, :, 0])
+            ios = self._policy_ios(env, buf, steps, logits, value)
+            sym = buf["sym"]
+            env.reset(out_symbolic=sym[0], frames=False)
+            for t in range(steps):
+                rp(env.render(sym[t], out=buf["policy_in"], blocked=True, dtype=torch.float32), out=heads)
+                env.policy_step(ios[t], out_symbolic=sym[t + 1], out=buf["rows"][t], frames=False)
+            rp(env.render(sym[steps], out=buf["policy_in"], blocked=True, dtype=torch.float32), out=heads)
+            buf["last_val"].copy_(value)
+            buf["_ios"] = ios  # the C structs must outlive a captured graph
+            return
         obs = buf["obs"]
         env.reset(out_obs=obs[0])
-        # shared weights do not change during the rollout: form the re-indexed first-layer kernels once, not per step
-        kw = {}
-        if self.use_cnn and getattr(policy, "blocked_first_layer", False):
-            if params is None:
-                kw["blocked"] = policy.blocked_weights()
-            else:  # per-task weights: the stacked re-indexed kernels, one pair per task
-                kw["blocked"] = tuple(vmap(_blocked_kernel)(params[f"{trunk}_extractor.network.0.weight"])
-                                      for trunk in ("actor", "critic"))
+        hv = buf["heads"].view(B, 2, 3)
+        logits, value = hv[:, 0], hv[:, 1, 0]
+        ios = self._policy_ios(env, buf, steps, logits, value)
         for t in range(steps):
-            a, lp, v = self._act(policy, params, obs[t], **kw)
-            env.step(a, out_obs=obs[t + 1], out=buf["rows"][t])
-            buf["act"][t].copy_(a); buf["logp"][t].copy_(lp); buf["val"][t].copy_(v)
-        buf["last_val"].copy_(self._act(policy, params, obs[steps], **kw)[2])
+            lg, v = self._logits_value(policy, params, obs[t])
+            logits.copy_(lg); value.copy_(v)
+            env.policy_step(ios[t], out_obs=obs[t + 1], out=buf["rows"][t])
+        buf["last_val"].copy_(self._logits_value(policy, params, obs[steps])[1])
+        buf["_ios"] = ios
+
+    def _logits_value(self, policy, params, obs):
+        """(logits `[B, 3]`, value `[B]`) for one frame per task, shared or per-task weights (generic path)."""
+        if params is None:
+            return policy(self._fmt(obs))
+        logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
+        return logits.squeeze(1), value.squeeze(1)
 
     @staticmethod
-    def _rollout_result(buf, steps):
+    def _rollout_result(env, buf, steps):
         ended = buf["ep_len"] > 0
-        return {"obs": buf["obs"][:steps], "act": buf["act"], "rew": buf["rew"], "val": buf["val"], "logp": buf["logp"],
-                "done": buf["done"], "last_val": buf["last_val"], "ep_lens": buf["ep_len"][ended].tolist(),
-                "ep_rews": buf["ep_ret"][ended].tolist()}
+        out = _Trajectory({"act": buf["act"], "rew": buf["rew"], "val": buf["val"], "logp": buf["logp"],
+                           "done": buf["done"], "last_val": buf["last_val"], "ep_lens": buf["ep_len"][ended].tolist(),
+                           "ep_rews": buf["ep_ret"][ended].tolist()})
+        if "sym" in buf:
+            out["obs_symbolic"] = buf["sym"][:steps]
+            out.env = env
+        else:
+            out["obs"] = buf["obs"][:steps]
+        return out
 
     def _collect_graphed(self, env, steps, params):
-        """The whole k-step rollout (policy forward, sampling, env step, stores) replayed from one CUDA graph per
-        (env, steps, shared | per-task weights).  Per-task weights are copied into the graph's static stacked tensors
-        before each replay; the meta-policy's own parameters are updated in place by the optimiser, so a graph over
-        them stays valid.  The returned tensors are the graph's buffers: valid until the next rollout of that kind."""
+        """The whole k-step rollout (input rendering, fused policy network, fused sample/step/store transition)
+        replayed from one CUDA graph per (env, steps, shared | per-task weights).  Per-task weights are copied into the
+        graph's static stacked tensors before each replay (the graph re-packs them); the meta-policy's own parameters
+        are updated in place by the optimiser, so a graph over them stays valid.  The returned tensors are the graph's
+        buffers: valid until the next rollout of that kind."""
         key = (id(env), steps, params is not None)
         g = self._graphs.get(key)
         if g is None:
@@ -158,7 +206,10 @@ class FOMAML:
             side = torch.cuda.Stream(env.device)
             side.wait_stream(torch.cuda.current_stream(env.device))
             with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
-                self._act(self.meta_policy, static, buf["obs"][0])
+                if "sym" in buf:
+                    RolloutPolicy(self.meta_policy, params=static)(buf["policy_in"].zero_())
+                else:
+                    self._logits_value(self.meta_policy, static, buf["obs"][0])
             torch.cuda.current_stream(env.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -169,18 +220,12 @@ class FOMAML:
             for n in static:
                 static[n].copy_(params[n])
         graph.replay()
-        return self._rollout_result(buf, steps)
+        return self._rollout_result(env, buf, steps)
 
     def _act(self, policy, params, obs, **kw):
-        """Sampled action, its log-probability and the value for one frame per task."""
-        if params is None:
-            return policy.act(self._fmt(obs), deterministic=False, **kw)
-        if "blocked" in kw:
-            logits, value = vmap(lambda p, o, wa, wc: _logits_value(policy, p, o.unsqueeze(0), blocked=(wa, wc)))(
-                params, self._fmt(obs), *kw["blocked"])
-        else:
-            logits, value = vmap(lambda p, o: _logits_value(policy, p, o.unsqueeze(0)))(params, self._fmt(obs))
-        logits, value = logits.squeeze(1), value.squeeze(1)
+        """Sampled action, its log-probability and the value for one frame per task (torch-side sampling: the
+        generic path for callers outside the fused rollouts)."""
+        logits, value = self._logits_value(policy, params, obs)
         logp_all = torch.log_softmax(logits, dim=-1)
         a = torch.multinomial(logp_all.exp(), 1).squeeze(-1)
         return a, logp_all.gather(-1, a.unsqueeze(-1)).squeeze(-1), value
@@ -227,15 +272,26 @@ class FOMAML:
         `params` (stacked per-task weights) task b is evaluated under its own weights."""
         adv, ret = self._advantages(batch)
         old_logp = batch["logp"].detach()
-        obs, act = batch["obs"], batch["act"]
+        act = batch["act"]
         if adv.dim() == 1:
-            new_logp, entropy, new_vals = policy.evaluate(obs, act)
+            new_logp, entropy, new_vals = policy.evaluate(batch["obs"], act)
         elif params is None:
             k, B = act.shape
-            new_logp, entropy, new_vals = policy.evaluate(self._fmt(obs.reshape((k * B,) + obs.shape[2:])), act.reshape(-1))
+            if "obs_symbolic" in batch:  # the first layer's float32 input, rendered from the stored symbolic images
+                flat = batch.env.render(batch["obs_symbolic"], blocked=True, dtype=torch.float32)
+            else:
+                obs = batch["obs"]
+                flat = self._fmt(obs.reshape((k * B,) + obs.shape[2:]))
+            new_logp, entropy, new_vals = policy.evaluate(flat, act.reshape(-1))
             new_logp, entropy, new_vals = new_logp.view(k, B), entropy.view(k, B), new_vals.view(k, B)
         else:
-            obs_b = self._fmt_tasks(obs)  # [B, k, ...]
+            if "obs_symbolic" in batch:  # task-major [B, k, 14, 14, 48]: gather + render + cast in one kernel
+                k, B = act.shape
+                index = (torch.arange(k, device=act.device).unsqueeze(0) * B + torch.arange(B, device=act.device).unsqueeze(1))
+                obs_b = batch.env.render(batch["obs_symbolic"], index.reshape(-1), blocked=True,
+                                         dtype=torch.float32).view(B, k, 14, 14, 48)
+            else:
+                obs_b = self._fmt_tasks(batch["obs"])  # [B, k, ...]
             logits, vals = vmap(lambda p, o: _logits_value(policy, p, o))(params, obs_b)
             logp_all = torch.log_softmax(logits, dim=-1)  # [B, k, A]
             entropy = (-(logp_all.exp() * logp_all).sum(-1)).t()
@@ -287,12 +343,9 @@ class FOMAML:
             loss, _ = self.compute_loss(support, meta, params=fast)
             fast = self._inner_step(fast, loss, names, lr)
 
-        def greedy(obs):
-            logits, _ = vmap(lambda p, o: _logits_value(meta, p, o.unsqueeze(0)))(fast, self._fmt(obs))
-            return logits.squeeze(1).argmax(-1)
-
         with torch.no_grad():
-            return evaluate_seeds(meta, self.sc_difficulty(), self.size, seeds, device=env.device, env=env, act_fn=greedy)
+            return evaluate_seeds(meta, self.sc_difficulty(), self.size, seeds, device=env.device, env=env,
+                                  params={n: p.detach() for n, p in fast.items()})
 
     # ---- meta step ----------------------------------------------------------------------------------------
     def meta_train_step(self, task_seeds, k_support=50, k_query=50):
@@ -344,6 +397,21 @@ class FOMAML:
         else:
             avg_rew, avg_steps = 0.0, float(k_query)
         return avg_loss, avg_rew, avg_steps, query_stats
+
+
+class _Trajectory(dict):
+    """The trajectory dict of `collect_trajectory`.  A fused rollout stores the 147-byte symbolic observations
+    (`obs_symbolic`, `[steps, B, 7, 7, 3]`); the reference's `obs` entry -- the frames the policy saw,
+    `[steps, B, 56, 56, 3]` uint8 -- is rendered from them the first time it is asked for."""
+    env = None
+
+    def __missing__(self, key):
+        if key == "obs" and "obs_symbolic" in self and self.env is not None:
+            sym = self["obs_symbolic"]
+            frames = self.env.render(sym.reshape(-1, 7, 7, 3)).view(sym.shape[:2] + (56, 56, 3))
+            self["obs"] = frames
+            return frames
+        raise KeyError(key)
 
 
 def _stack(policy, B):

@@ -42,15 +42,40 @@ class FlatGrads:
             p.grad = self.flat[off: off + p.numel()].view_as(p)
             off += p.numel()
 
+        self.timing = None  # list of (start, end) CUDA events once enable_timing() was called
+
     def zero_(self):
         self.flat.zero_()
+
+    def enable_timing(self, on=True):
+        """Bracket every gradient all-reduce with CUDA events (measurement only: `collective_seconds()` sums them)."""
+        self.timing = [] if on else None
+
+    def collective_seconds(self, clear=True):
+        """Device time spent inside the gradient all-reduces since the last call (synchronises)."""
+        if not self.timing:
+            return 0.0
+        torch.cuda.synchronize(self.flat.device)
+        total = sum(a.elapsed_time(b) for a, b in self.timing) * 1e-3
+        if clear:
+            self.timing = []
+        return total
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
 
     def all_reduce_mean(self):
         """Average over ranks (each rank's loss is a mean over its own equally sized shard)."""
         w = world_size()
         if w > 1:
+            if self.timing is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(w)
+            if self.timing is not None:
+                b.record()
+                self.timing.append((a, b))
 
     def all_reduce_sum(self):
         if world_size() > 1:

@@ -3,9 +3,11 @@ update math; only the data path is rewired).
 
 Two rollout paths behind `collect_rollouts()`:
   * a BatchedMerlinEnv (N envs, one fused CUDA launch per step): observations are rendered by the env kernel
-    straight into the `[T, N, 56, 56, 3]` uint8 rollout buffer, actions come from one batched policy forward,
-    nothing crosses PCIe and nothing synchronises until the rollout is over; optionally the whole T-step loop
-    is replayed from one CUDA graph.  `batch_size` = T * N transitions per rollout.
+    straight into the rollout buffer, the policy is evaluated once per step for all envs, and the rest of the
+    transition -- sample the action, its log-probability, the three rollout stores, the env step, the next
+    observation -- is ONE launch (`BatchedMerlinEnv.policy_step`, merlin_env_policy_step).  Nothing crosses PCIe and
+    nothing synchronises until the rollout is over; optionally the whole T-step loop is replayed from one CUDA
+    graph.  `batch_size` = T * N transitions per rollout.
   * the reference's single-env wrapper stack (`ScenarioCreator.create_env`): the same per-step loop as the
     reference (src/ppo.py:64-105), one env, host observations -- kept so existing scripts run unchanged.
 GAE always runs in the CUDA kernel (`merlin_b200.gae`).  With `torch.distributed` initialised, every rank rolls
@@ -21,14 +23,14 @@ from merlin_b200 import BatchedMerlinEnv, gae as gae_kernel
 from src.metrics.ppo_metrics import aggregate_ppo_update_metrics
 
 from . import parallel
-from .actor_critic import CNNActorCritic, MLPActorCritic
+from .actor_critic import CNNActorCritic, MLPActorCritic, RolloutPolicy
 from .rollout_buffer import RolloutBuffer
 
 
 class PPO:
     def __init__(self, env, lr=3e-4, gamma=0.99, lam=0.95, clip_eps=0.2, update_epochs=10, batch_size=2048,
                  minibatch_size=256, vf_coef=0.5, ent_coef=0.01, device="cpu", use_cuda_graph=False,
-                 obs_storage="rgb", amp_dtype=None, minibatch_frames=torch.float32):
+                 obs_storage="rgb", amp_dtype=None, minibatch_frames=torch.float32, carry_episodes=None):
         self.env = env
         self.batched = isinstance(env, BatchedMerlinEnv)
         self.device = env.device if self.batched else torch.device(device)
@@ -96,6 +98,21 @@ class PPO:
             self._rows = [env.make_step_buffers(reward=row(self.buffer.rewards, t), done=row(self.buffer.dones, t),
                                                 episode_return=self._ep_ret[t], episode_length=self._ep_len[t], **scratch)
                           for t in range(T)]
+            # one fused transition per step: logits / value of step t -> action, log-probability, value rows of the buffer
+            self._heads = torch.zeros((2, N, act_dim), dtype=torch.float32, device=self.device)
+            self._ios = [env.make_policy_io(self._heads[0], self._heads[1, :, 0], action=row(self.buffer.actions, t),
+                                            logprob=row(self.buffer.logprobs, t), value_out=row(self.buffer.values, t))
+                         for t in range(T)]
+            self._rollout_policy = None
+        # carry_episodes: a rollout continues the episodes the previous one left unfinished (the usual vectorised-PPO
+        # regime) instead of starting from a fresh reset() like the reference's single-env loop (src/ppo.py:65).  With a
+        # horizon shorter than the episode cap a fresh reset per rollout would only ever show the policy the first T steps
+        # of an episode and would log only the episodes that finished within T steps.  None = automatic: carry exactly then.
+        if carry_episodes is None:
+            carry_episodes = self.batched and self.buffer.horizon < env.max_steps
+        self.carry_episodes = bool(carry_episodes) and self.batched
+        self._started = False
+        self.unfinished_episodes = 0   # envs in the middle of an episode when the last rollout ended
         self.use_cuda_graph = bool(use_cuda_graph) and self.batched
         self._graph = None
 
@@ -110,57 +127,84 @@ class PPO:
     # ---- rollouts -----------------------------------------------------------------------------------------
     def collect_rollouts(self):
         """One rollout of `batch_size` transitions; returns the bootstrap value (`float` for a single env, a
-        `[N]` device tensor for a batched env).  Like the reference it starts from a fresh `reset()`."""
+        `[N]` device tensor for a batched env).  The single-env path starts from a fresh `reset()` like the reference;
+        the batched path continues unfinished episodes when `carry_episodes` (see __init__)."""
         return self._collect_batched() if self.batched else self._collect_single()
 
-    def _rollout_body(self):
+    def _logits_value_into_heads(self, x, lean):
+        """Policy outputs for `x` written to the static `[2, N, A]` head tensor the fused transitions read."""
+        if lean:
+            if x.dtype == torch.uint8:  # stored frames [N, 56, 56, 3]: to the blocked float layout the fused network reads
+                n = x.shape[0]
+                x = x.reshape(n, 14, 4, 14, 4, 3).permute(0, 1, 3, 5, 2, 4).reshape(n, 14, 14, 48).float()
+            self._rollout_policy(x, out=self._heads)
+        else:
+            logits, value = self.ac(x)
+            self._heads[0].copy_(logits)
+            self._heads[1, :, 0].copy_(value)
+
+    def _rollout_body(self, fresh):
         env, buf, T = self.env, self.buffer, self.buffer.horizon
         sym = self.obs_storage == "symbolic"
-        # the parameters do not change during a rollout: the re-indexed first-layer kernels are formed once
-        w = self.ac.blocked_weights() if self.use_cnn and self.ac.blocked_first_layer else None
-        kw = {} if w is None else {"blocked": w}
-        if sym:
-            # symbolic storage: the step kernel writes the 147-byte images straight into the rollout and NO frames (the
-            # symbolic-only kernel runs); the policy's float32 input is rendered from the image it is about to act on
-            def policy_input(t):
-                src = buf.obs_slot(t) if t < T else self._last_sym
-                return env.render(src, out=self._policy_in, blocked=True, dtype=torch.float32)
-            env.reset(out_symbolic=buf.obs_slot(0), frames=False)
-        else:
-            def policy_input(t):
-                return buf.obs_slot(t) if t < T else self._last_obs
-            env.reset(out_obs=buf.obs_slot(0))
-        for t in range(T):
-            action, logp, value = self.ac.act(policy_input(t), deterministic=False, **kw)
-            if sym:
-                env.step(action, out_symbolic=buf.obs_slot(t + 1) if t + 1 < T else self._last_sym, out=self._rows[t],
-                         frames=False)
+        lean = self.use_cnn and self.ac.blocked_first_layer
+        if lean:
+            # the parameters do not change during a rollout: both trunks are packed once into one fused network
+            if self._rollout_policy is None:
+                self._rollout_policy = RolloutPolicy(self.ac)
             else:
-                env.step(action, out_obs=buf.obs_slot(t + 1) if t + 1 < T else self._last_obs, out=self._rows[t])
-            shape = buf.actions[t].shape  # [N], or [] for a single batched env (the reference's [T] buffers)
-            buf.actions[t].copy_(action.reshape(shape))
-            buf.logprobs[t].copy_(logp.reshape(shape))
-            buf.values[t].copy_(value.reshape(shape))
-        self._last_value.copy_(self.ac.act(policy_input(T), **kw)[2])
+                self._rollout_policy.refresh()
+        last = self._last_sym if sym else self._last_obs
+        if fresh:
+            if sym:
+                env.reset(out_symbolic=buf.obs_slot(0), frames=False)
+            else:
+                env.reset(out_obs=buf.obs_slot(0))
+        else:  # continue the running episodes: the observation the last rollout ended on opens this one
+            buf.obs_slot(0).copy_(last)
+
+        def policy_input(t):
+            src = buf.obs_slot(t) if t < T else last
+            if sym:  # the policy's float32 input is rendered from the 147-byte image it is about to act on
+                return env.render(src, out=self._policy_in, blocked=True, dtype=torch.float32)
+            return src
+
+        for t in range(T):
+            self._logits_value_into_heads(policy_input(t), lean)
+            nxt = buf.obs_slot(t + 1) if t + 1 < T else last
+            if sym:  # symbolic storage: the symbolic-only kernel runs and writes NO frames
+                env.policy_step(self._ios[t], out_symbolic=nxt, out=self._rows[t], frames=False)
+            else:
+                env.policy_step(self._ios[t], out_obs=nxt, out=self._rows[t])
+        self._logits_value_into_heads(policy_input(T), lean)
+        self._last_value.copy_(self._heads[1, :, 0])
 
     @torch.no_grad()
     def _collect_batched(self):
+        fresh = not (self.carry_episodes and self._started)
         if self.use_cuda_graph:
-            if self._graph is None:
+            if self._graph is None or self._graph[0] != fresh:
                 side = torch.cuda.Stream(self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):  # warm-up outside capture (cuDNN plans, allocator)
-                    self.ac.act(self._policy_in if self.obs_storage == "symbolic" else self._last_obs)
+                    x = self._policy_in if self.obs_storage == "symbolic" else self._last_obs
+                    lean = self.use_cnn and self.ac.blocked_first_layer
+                    if lean and self._rollout_policy is None:
+                        self._rollout_policy = RolloutPolicy(self.ac)
+                    self._logits_value_into_heads(x, lean)
                 torch.cuda.current_stream(self.device).wait_stream(side)
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
-                    self._rollout_body()
-            self._graph.replay()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._rollout_body(fresh)
+                self._graph = (fresh, graph)
+            self._graph[1].replay()
         else:
-            self._rollout_body()
+            self._rollout_body(fresh)
+        self._started = True
         ended = self._ep_len > 0  # one synchronisation per rollout, for the episode logs
         self.episode_returns.extend(self._ep_ret[ended].tolist())
         self.episode_lengths.extend(self._ep_len[ended].tolist())
+        # episodes cut by the end of the rollout: continued next time (carry_episodes) or discarded by the next reset
+        self.unfinished_episodes = int((self.buffer.dones[-1].reshape(-1) == 0).sum().item())
         return self._last_value
 
     def _collect_single(self):

@@ -110,7 +110,7 @@ class ScenarioCreator:
                                max_steps=env_kwargs.pop("max_steps", params.get("max_steps")), device=device,
                                reset_mode="same" if fomaml_mode else "next", stuck_penalty=stuck_penalty,
                                exploration_bonus=exploration_bonus, want_symbolic=want_symbolic, **env_kwargs)
-        env.difficulty, env.size = diff, size
+        env.difficulty = diff
         return env
 
     # ---- accessors --------------------------------------------------------------------------------------

@@ -72,16 +72,16 @@ int hm_step(int N, int W, int H, int max_steps, int cell_stride, int n_actions, 
 // The row-parallel observation (obs_swar.cuh) for N envs: symbolic image u8[N][147] and tile kinds u8[N][49], to be
 // compared with what hm_step produced by the per-cell form.  W >= 7; `cells` needs 8 bytes of slack after the last grid.
 int hm_observe_swar(int N, int W, int H, int cell_stride, const int32_t* state, const uint8_t* cells,
-                    const uint8_t* atlas, uint8_t* obs_rgb, uint8_t* obs_sym) {
+                    const uint8_t* atlas, uint8_t* obs_rgb, uint8_t* obs_sym, int doors) {
   for (int e = 0; e < N; ++e) {
     EnvState s{};
     const int32_t* st = state + 4 * e;
     unpack_state(st[0], st[1], st[2], st[3], s);
     uint64_t g[kView], seen[kView];
-    observe_swar(s, cells + (size_t)e * cell_stride, W, H, g, seen);
+    observe_swar(s, cells + (size_t)e * cell_stride, W, H, g, seen, doors != 0);
     for (int vi = 0; vi < kView; ++vi) {
       uint32_t w[6];
-      encode_group(g[vi], w);
+      encode_group(g[vi], w, doors != 0);
       memcpy(obs_sym + (size_t)e * kSymBytes + vi * 21, w, 21);
     }
     uint32_t kw[13];
@@ -98,7 +98,30 @@ int hm_observe_swar(int N, int W, int H, int cell_stride, const int32_t* state, 
   return 0;
 }
 
+// The in-kernel action sampler (env_logic.cuh: philox4x32_10_x0, sampler_uniform, sample_policy) for N envs.
+void hm_philox(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4) {
+  philox4x32_10_x0(counter4[0], counter4[1], counter4[2], counter4[3], key2[0], key2[1], out4);
+}
+int hm_sample(int N, int n_actions, const float* logits, uint64_t seed, const uint32_t* draws, int greedy,
+              int64_t* action, float* logp, float* uniform) {
+  for (int e = 0; e < N; ++e) {
+    float lg[kMaxActions];
+    for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? logits[(size_t)e * n_actions + a] : 0.f;
+    const float u = greedy ? 0.f : sampler_uniform((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)e, draws[e]);
+    const PolicySample s = sample_policy(lg, n_actions, u, greedy != 0);
+    action[e] = s.action; logp[e] = s.logp; uniform[e] = u;
+  }
+  return 0;
+}
+
 // Grid.process_vis on a 49-bit transparency mask (bit vj*7 + vi), for the property tests.
 unsigned long long hm_visibility(unsigned long long transp) { return merlin::visibility(transp); }
+unsigned long long hm_visibility_literal(unsigned long long transp) { return merlin::visibility_literal(transp); }
+// One process_vis row, both forms: returns lit | next_seed << 8.
+unsigned hm_vis_row(unsigned seed, unsigned T, int literal) {
+  uint32_t lit = 0;
+  const uint32_t next = literal ? merlin::vis_row_literal(seed, T, lit) : merlin::vis_row(seed, T, lit);
+  return lit | (next << 8);
+}
 
 }  // extern "C"

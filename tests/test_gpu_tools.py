@@ -38,9 +38,18 @@ def test_train_fomaml_tool_tiny(tmp_path):
 
 
 def test_bench_tool_small_batch():
-    lines = _run(["bench.py", "--envs", "32768", "--steps", "16", "--warmup", "3", "--layouts", "256", "--skip-cpu-baseline"])
+    lines = _run(["bench.py", "--envs", "32768", "--steps", "16", "--warmup", "3", "--layouts", "256", "--skip-cpu-baseline",
+                  "--ppo-envs", "64", "--ppo-horizon", "8", "--ppo-iters", "1", "--fomaml-tasks", "4", "--fomaml-k", "16",
+                  "--fomaml-iters", "1"])
     assert len(lines) == 1  # ONE JSON line on stdout
     out = json.loads(lines[0])
+    # the learner sections (BASELINE metric's second half; configs 3 and 4), every N
+    assert out["ppo"]["value"] > 0 and out["ppo"]["unit"] == "env-steps/s" and out["ppo"]["allreduce_bytes"] == 744772 * 4
+    assert {"rollout_s", "update_s", "allreduce_s"} <= set(out["ppo"])
+    assert out["fomaml"]["strong"]["s_per_iteration"] > 0 and out["fomaml"]["strong"]["tasks_per_gpu"] == 4
+    # clocks are sampled in-process: a 16-step timed region still holds samples
+    assert out["clocks"]["samples"] >= 1 and out["clocks"]["sm_mhz"] > 0
+    assert out["config"]["layout_pool"] == 256 and out["config"]["envs_restarted_on_a_new_layout_in_timed_region_rank0"] > 0
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e"):
         assert key in out, key

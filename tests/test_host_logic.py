@@ -121,9 +121,14 @@ class HostModelEnv:
         if self.W >= 7:
             rgb2, sym2 = np.zeros_like(rgb), np.zeros_like(sym)
             padded = np.concatenate([self.cells.reshape(-1), np.zeros(8, np.uint8)])
-            self.lib.hm_observe_swar(N, self.W, self.H, self.stride, p(self.state), p(padded), p(self.atlas), p(rgb2), p(sym2))
-            assert np.array_equal(sym2, sym), "obs_swar symbolic image differs from the per-cell form"
-            assert np.array_equal(rgb2, rgb), "obs_swar tile kinds differ from the per-cell form"
+            # grids without closed / locked doors also go through the short path the kernels take for door-free pools
+            has_doors = bool(np.isin(self.cells & 0xF, (11, 12)).any())
+            for doors in ((1,) if has_doors else (1, 0)):
+                rgb2.fill(0); sym2.fill(0)
+                self.lib.hm_observe_swar(N, self.W, self.H, self.stride, p(self.state), p(padded), p(self.atlas), p(rgb2),
+                                         p(sym2), doors)
+                assert np.array_equal(sym2, sym), f"obs_swar symbolic image differs from the per-cell form (doors={doors})"
+                assert np.array_equal(rgb2, rgb), f"obs_swar tile kinds differ from the per-cell form (doors={doors})"
         return rgb, sym, rew, te.astype(bool), tr.astype(bool), sk.astype(bool)
 
 
@@ -222,6 +227,96 @@ def test_visibility_bitmask_exhaustive_rows():
         rgb, sym, *_ = hm.call(a, do_step=True)
         assert np.array_equal(sym, info["obs_symbolic"])
         assert np.array_equal(rgb, rgb0)
+
+
+def test_visibility_row_carry_chain_form_equals_literal_sweeps_exhaustively():
+    """vis_row (one addition per sweep) == vis_row_literal (six propagation steps per sweep, the upstream loops) for
+    ALL 128 x 128 (lit-from-below, transparency) rows, and visibility == visibility_literal on random 49-bit masks."""
+    lib = _host_model()
+    lib.hm_vis_row.restype = ctypes.c_uint32
+    lib.hm_vis_row.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+    for seed in range(128):
+        for T in range(128):
+            assert lib.hm_vis_row(seed, T, 0) == lib.hm_vis_row(seed, T, 1), (seed, T)
+    lib.hm_visibility.restype = lib.hm_visibility_literal.restype = ctypes.c_uint64
+    lib.hm_visibility.argtypes = lib.hm_visibility_literal.argtypes = [ctypes.c_uint64]
+    rng = np.random.default_rng(7)
+    for dens in (0.2, 0.5, 0.8, 0.95):
+        for _ in range(5000):
+            m = int(sum(1 << i for i in np.nonzero(rng.random(49) < dens)[0]))
+            assert lib.hm_visibility(m) == lib.hm_visibility_literal(m), m
+
+
+# ---- in-kernel action sampler (env_logic.cuh: Philox4x32-10, inverse CDF) -------------------------------------
+PHILOX_KAT = [  # Random123 known-answer vectors for philox4x32-10: (counter, key, output)
+    ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+    ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+]
+
+
+def test_philox_known_answers_oracle_and_kernel_header():
+    from oracle import sampler
+    lib = _host_model()
+    for ctr, key, want in PHILOX_KAT:
+        assert sampler.philox4x32_10(ctr, key) == want
+        c, k, o = (ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), (ctypes.c_uint32 * 4)()
+        lib.hm_philox(c, k, o)
+        assert tuple(o) == want
+
+
+def _hm_sample(logits, seed, draws, greedy=False):
+    lib = _host_model()
+    N, A = logits.shape
+    lib.hm_sample.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    logits = np.ascontiguousarray(logits, np.float32)
+    draws = np.ascontiguousarray(draws, np.uint32)
+    act, lp, u = np.zeros(N, np.int64), np.zeros(N, np.float32), np.zeros(N, np.float32)
+    lib.hm_sample(N, A, logits.ctypes.data, seed, draws.ctypes.data, int(greedy), act.ctypes.data, lp.ctypes.data, u.ctypes.data)
+    return act, lp, u
+
+
+@pytest.mark.parametrize("A", [3, 7])
+def test_sampler_header_matches_oracle_restatement(A):
+    """sample_policy / sampler_uniform as the kernels compile them (host build) vs the independent numpy restatement:
+    identical uniforms, identical actions (away from CDF boundaries), log-probabilities to float32 rounding."""
+    from oracle import sampler
+    rng = np.random.default_rng(A)
+    N, seed = 4000, 0x1234_5678_9ABC_DEF0
+    logits = (rng.standard_normal((N, A)) * rng.choice([0.01, 1.0, 5.0], (N, 1))).astype(np.float32)
+    draws = rng.integers(0, 1 << 20, N)
+    act, lp, u = _hm_sample(logits, seed, draws)
+    assert np.array_equal(u, np.array([sampler.uniform(seed, e, int(draws[e])) for e in range(N)], np.float32))
+    assert (u >= 0).all() and (u < 1).all()
+    ract, rlp, margin = sampler.sample_batch(logits, seed, draws)
+    safe = margin > 1e-5
+    assert safe.mean() > 0.99
+    assert np.array_equal(act[safe], ract[safe])
+    same = act == ract
+    assert np.allclose(lp[same], rlp[same], rtol=0, atol=2e-6)
+    ref_lp = logits - logits.max(1, keepdims=True)
+    ref_lp = ref_lp - np.log(np.exp(ref_lp.astype(np.float64)).sum(1, keepdims=True))
+    assert np.allclose(lp, ref_lp[np.arange(N), act], atol=3e-6)
+    g_act, g_lp, _ = _hm_sample(logits, seed, draws, greedy=True)
+    assert np.array_equal(g_act, logits.argmax(1))
+    assert np.allclose(g_lp, ref_lp[np.arange(N), g_act], atol=3e-6)
+
+
+def test_sampler_frequencies_follow_softmax():
+    """Chi-square of the sampled action counts against softmax(logits): one fixed logit row, 60k independent draws
+    (env index and draw number both vary)."""
+    logits = np.tile(np.array([[0.3, -1.2, 1.1]], np.float32), (60000, 1))
+    p = np.exp(logits[0].astype(np.float64)); p /= p.sum()
+    draws = np.arange(60000) % 7
+    act, _, _ = _hm_sample(logits, 99, draws)
+    counts = np.bincount(act, minlength=3)
+    chi2 = float(((counts - 60000 * p) ** 2 / (60000 * p)).sum())
+    assert chi2 < 18.4  # chi-square, 2 degrees of freedom: p = 1e-4
+    # degenerate rows never leave the action range
+    weird = np.array([[np.inf, 0, 0], [-np.inf, -np.inf, -np.inf], [np.nan, 0, 0], [1e30, -1e30, 0]], np.float32)
+    a, _, _ = _hm_sample(weird, 1, np.zeros(4))
+    assert ((a >= 0) & (a < 3)).all()
 
 
 # ---- property tests (hypothesis): arbitrary W x H rooms, full object set, arbitrary action strings ----------------
