@@ -132,22 +132,33 @@ class ClockSampler:
         if self.nvml is None or t0 is None or t1 is None:
             return None
         # a region shorter than the polling period still owns the sample taken just after it started
-        inside = [x for x in self.samples if t0 <= x[0] <= t1 + 0.012]
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        nearest_ms = None
+        if not inside and self.samples:
+            # a region shorter than one polling period: the sample closest to it in time stands in (and says so)
+            x = min(self.samples, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))
+            nearest_ms = 1e3 * min(abs(x[0] - t0), abs(x[0] - t1))
+            inside = [x]
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "samples": 0, "reasons": ["no samples"]}
         bits = 0
         for x in inside:
             bits |= x[3]
-        return {"sm_mhz": statistics.median(x[1] for x in inside), "sm_max_mhz": self.max_sm,
-                "power_w_max": max(x[2] for x in inside), "samples": len(inside),
-                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k)}
+        out = {"sm_mhz": statistics.median(x[1] for x in inside), "sm_max_mhz": self.max_sm,
+               "power_w_max": max(x[2] for x in inside), "samples": len(inside),
+               "reasons": sorted(v for k, v in self.REASONS.items() if bits & k)}
+        if nearest_ms is not None:
+            out["nearest_sample_ms_from_region"] = nearest_ms
+        return out
 
     def stop(self):
         if self.nvml is not None:
             self.stop_flag = True
             self.thread.join(timeout=1.0)
             out = self.region("timed") or {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
-            out["source"] = "NVML in-process, 10 ms period, samples inside the device-timed region"
+            out["source"] = "NVML in-process (one sample per ~10 ms), samples inside the device-timed region"
+            if self.region("timed"):
+                out["region_ms"] = 1e3 * (self.marks["timed_end"] - self.marks["timed_start"])
             for extra in ("ppo", "fomaml"):
                 r = self.region(extra)
                 if r:
@@ -389,8 +400,11 @@ def bench_fomaml(args, dev, rank, world, sampler, barrier):
             fo.meta_train_step(batch(), k_support=k, k_query=k)
         barrier()
         t0 = time.perf_counter()
+        nxt = batch()
         for _ in range(args.fomaml_iters):
-            fo.meta_train_step(batch(), k_support=k, k_query=k)
+            cur, nxt = nxt, batch()
+            fo.prefetch_tasks(nxt)  # next meta-batch's layouts: host thread, overlapped with this iteration's GPU work
+            fo.meta_train_step(cur, k_support=k, k_query=k)
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -94,7 +94,11 @@ typedef struct merlin_env_config {
 
 /* Optional outputs of step(); any pointer may be NULL. */
 typedef struct merlin_step_extras {
-  float* episode_return;   /* [N] sum of rewards of the episode that ended this step, else 0 */
+  float* episode_return;   /* [N] sum of rewards of the episode that ended this step, else 0.  Accumulated on the device in
+                              float32, one rounding per step; the reference sums Python floats, i.e. float64
+                              (src/ppo.py:88, src/fomaml.py:76).  A logging quantity only -- rewards themselves are formed in
+                              float64 and rounded once, bit-identical to the reference's float32 buffer entries -- and the
+                              two sums agree to ~1e-7 relative per step (tests/helpers.py compares them at 1e-5) */
   int32_t* episode_length; /* [N] its length, else 0 */
   uint8_t* stuck;          /* [N] info["stuck"] of StuckPenaltyWrapper */
   float* done;             /* [N] 1.0f where terminated or truncated, else 0.0f: the `done` the reference's learners store

@@ -73,6 +73,27 @@ struct ActionDraw {
   float logp;
   uint32_t draw;
 };
+// The sampling itself is kept OUT of line: the frame kernels' state phase runs under a 128-register cap, and with this
+// code inlined next to it the register allocation of the hot (actions given) path degrades -- measured on B200 at 1M
+// envs: 1461 us per step inlined vs 1435 us without the policy code (profiles/r02_tile_kernel_ab.txt).
+__device__ __noinline__ void draw_action_from_logits(const float* __restrict__ logits, const uint32_t* __restrict__ draws,
+                                                      int n_actions, int stride, uint32_t seed_lo, uint32_t seed_hi, int greedy,
+                                                      int e, ActionDraw* out) {
+  float lg[kMaxActions];
+  const float* row = logits + (size_t)e * stride;
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? row[a] : 0.f;
+  float u = 0.f;
+  uint32_t draw = 0;
+  if (!greedy) {
+    draw = draws[e];
+    u = sampler_uniform(seed_lo, seed_hi, (uint32_t)e, draw);
+  }
+  const PolicySample smp = sample_policy(lg, n_actions, u, greedy != 0);
+  out->action = smp.action;
+  out->logp = smp.logp;
+  out->draw = draw;
+}
 __device__ __forceinline__ ActionDraw draw_action(const EnvParams& p, int n_actions, int e) {
   ActionDraw d;
   d.logp = 0.f;
@@ -81,26 +102,21 @@ __device__ __forceinline__ ActionDraw draw_action(const EnvParams& p, int n_acti
     d.action = p.actions[e];
     return d;
   }
-  float lg[kMaxActions];
-  const float* row = p.logits + (size_t)e * p.logits_stride;
-#pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? row[a] : 0.f;
-  float u = 0.f;
-  if (!p.greedy) {
-    d.draw = p.draws[e];
-    u = sampler_uniform(p.seed_lo, p.seed_hi, (uint32_t)e, d.draw);
-  }
-  const PolicySample smp = sample_policy(lg, n_actions, u, p.greedy != 0);
-  d.action = smp.action;
-  d.logp = smp.logp;
+  draw_action_from_logits(p.logits, p.draws, n_actions, p.logits_stride, p.seed_lo, p.seed_hi, p.greedy, e, &d);
   return d;
+}
+__device__ __noinline__ void commit_action_rows(int64_t* out_action, float* out_logp, float* out_value, const float* value_in,
+                                                int value_stride, uint32_t* draws, int greedy, int e, long long action,
+                                                float logp, uint32_t draw) {
+  if (!greedy) draws[e] = draw + 1u;
+  out_action[e] = action;
+  out_logp[e] = logp;
+  if (out_value) out_value[e] = value_in[(size_t)e * value_stride];
 }
 __device__ __forceinline__ void commit_action(const EnvParams& p, int e, const ActionDraw& d) {
   if (p.logits == nullptr) return;
-  if (!p.greedy) p.draws[e] = d.draw + 1u;
-  p.out_action[e] = d.action;
-  p.out_logp[e] = d.logp;
-  if (p.out_value) p.out_value[e] = p.value_in[(size_t)e * p.value_stride];
+  commit_action_rows(p.out_action, p.out_logp, p.out_value, p.value_in, p.value_stride, p.draws, p.greedy, e, d.action,
+                     d.logp, d.draw);
 }
 // First-episode record of deterministic evaluation (see EnvParams::rec_finished).
 __device__ __forceinline__ void record_first_episode(const EnvParams& p, int e, bool done, bool goal, float ep_ret, int len) {
@@ -698,13 +714,16 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, c
 //     588-entry chunk map (ncu at 4096 envs, profiles/r02_warp_kernel_ncu.md: 1390 -> ~650 warp instructions per env).
 //     The kinds are kept premultiplied (kind * 192, the tile's byte offset in the atlas) as 16-bit words.
 //   * atlas staging touches only the slots the pool can show: thread t tests tile t / 2 and copies half of it.
-constexpr int kWarpKernelThreads = 256;
+#ifndef MERLIN_WARP_THREADS
+#define MERLIN_WARP_THREADS 256
+#define MERLIN_WARP_CTAS 4
+#endif
+constexpr int kWarpKernelThreads = MERLIN_WARP_THREADS;
 constexpr int kWarpKindBytes = 128;          // 49 premultiplied kinds (u16) per warp, padded
 constexpr int kPairChunks = 2 * kUnitsPerRow / 2;   // 21 16-byte chunks per pair of pixel rows
-constexpr int kRowPairs = kView * kTile / 2;        // 28
 
 template <bool STEP>
-__global__ void __launch_bounds__(kWarpKernelThreads, 4) env_kernel_warp(const EnvParams p) {
+__global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kernel_warp(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -722,12 +741,15 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 4) env_kernel_warp(const E
     if (STEP && p.logits == nullptr) act_next = p.actions[e];
   }
   if (f.want_rgb) {
-    const int tile = threadIdx.x >> 1, half = threadIdx.x & 1;   // 256 threads = 128 tiles x 2 halves of 6 int4
-    if (tile < kAtlasTiles && tile_bit(p.tile_present, tile)) {
-      const int4* src = reinterpret_cast<const int4*>(p.atlas) + tile * (kTileBytes / 16) + half * 6;
-      int4* dst = reinterpret_cast<int4*>(atlas_s) + tile * (kTileBytes / 16) + half * 6;
+    // thread t tests tile t / 2 and copies half of it (6 int4); a 128-thread CTA takes two rounds
+    for (int t = threadIdx.x; t < 2 * kAtlasTiles; t += kWarpKernelThreads) {
+      const int tile = t >> 1, half = t & 1;
+      if (tile_bit(p.tile_present, tile)) {
+        const int4* src = reinterpret_cast<const int4*>(p.atlas) + tile * (kTileBytes / 16) + half * 6;
+        int4* dst = reinterpret_cast<int4*>(atlas_s) + tile * (kTileBytes / 16) + half * 6;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) dst[i] = __ldg(src + i);
+        for (int i = 0; i < 6; ++i) dst[i] = __ldg(src + i);
+      }
     }
   }
   __syncthreads();
@@ -1029,6 +1051,45 @@ __global__ void __launch_bounds__(kRenderF32Threads, 3) render_f32_kernel(const 
   }
   __syncthreads();
 
+  // one frame's float4 chunk f: one u16 map read (shared by 4 lanes), one slot read, one 16-byte atlas read, one store
+  auto emit_chunk = [&](const uint8_t* kpw, float* frame, int f) {
+    const uint32_t q = map_s[f >> 2];
+    const uint32_t cell = q & 0xff, off = (q >> 8) * 16 + (f & 3) * 4;   // element offset inside the tile
+    const uint32_t slot = kpw[cell];
+    float4 v;
+    if (slot != 255) {
+      v = *reinterpret_cast<const float4*>(atlas_f + slot * kTileBytes + off);
+    } else {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.atlas + (uint32_t)kpw[64 + cell] * kTileBytes + off));
+      v = make_float4(pixel_f32(w & 0xff, normalise), pixel_f32((w >> 8) & 0xff, normalise),
+                      pixel_f32((w >> 16) & 0xff, normalise), pixel_f32(w >> 24, normalise));
+    }
+    st_stream_v4(frame + f * 4, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+  };
+  auto load_kinds = [&](uint8_t* kpw, int m, int t) {   // thread t < 64 of the caller's group handles cells t (and < 49)
+    long long row = p.index ? p.index[m] : m;
+    if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;
+    const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
+    if (t < kCells) {
+      const uint32_t kind = kind_of_sym(sym[3 * t], sym[3 * t + 1], sym[3 * t + 2], t == (kView / 2) * kView + (kView - 1));
+      kpw[t] = slot_s[kind];
+      kpw[64 + t] = (uint8_t)kind;
+    }
+  };
+
+  if (p.frame_per_cta) {
+    // few frames (a policy-input render for a small batch: launch latency is what counts): one CTA per frame, all
+    // eight warps share its 2352 chunks -- 10 chunk rounds per thread instead of 74 per lane
+    for (int m = blockIdx.x; m < p.M; m += gridDim.x) {
+      __syncthreads();  // kp of the previous frame has been consumed
+      load_kinds(kp - warp * 128, m, threadIdx.x);
+      __syncthreads();
+      float* frame = p.out_f32 + (size_t)m * kImgBytes;
+      for (int f = threadIdx.x; f < kF32Chunks; f += kRenderF32Threads) emit_chunk(kp - warp * 128, frame, f);
+    }
+    return;
+  }
+
   __shared__ int s_next;
   const int n_groups = (p.M + kRenderF32Group - 1) / kRenderF32Group;
   if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
@@ -1038,37 +1099,14 @@ __global__ void __launch_bounds__(kRenderF32Threads, 3) render_f32_kernel(const 
     __syncthreads();  // everyone has read the ticket
     if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
     for (int m = group * kRenderF32Group + warp; m < min(p.M, (group + 1) * kRenderF32Group); m += warps_per_cta) {
-      long long row = p.index ? p.index[m] : m;
-      if (p.n_rows && (row < 0 || row >= p.n_rows)) row = 0;
-      const uint8_t* sym = p.sym + (size_t)row * kSymBytes;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k = lane + 32 * h;
-        if (k < kCells) {
-          const uint32_t kind = kind_of_sym(sym[3 * k], sym[3 * k + 1], sym[3 * k + 2], k == (kView / 2) * kView + (kView - 1));
-          kp[k] = slot_s[kind];
-          kp[64 + k] = (uint8_t)kind;
-        }
-      }
+      load_kinds(kp, m, lane);
+      load_kinds(kp, m, lane + 32);
       __syncwarp();
       float* frame = p.out_f32 + (size_t)m * kImgBytes;
 #pragma unroll 4
       for (int k = 0; k < kF32Iters; ++k) {
         const int f = lane + 32 * k;
-        if (f < kF32Chunks) {
-          const uint32_t q = map_s[f >> 2];
-          const uint32_t cell = q & 0xff, off = (q >> 8) * 16 + (f & 3) * 4;   // element offset inside the tile
-          const uint32_t slot = kp[cell];
-          float4 v;
-          if (slot != 255) {
-            v = *reinterpret_cast<const float4*>(atlas_f + slot * kTileBytes + off);
-          } else {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.atlas + (uint32_t)kp[64 + cell] * kTileBytes + off));
-            v = make_float4(pixel_f32(w & 0xff, normalise), pixel_f32((w >> 8) & 0xff, normalise),
-                            pixel_f32((w >> 16) & 0xff, normalise), pixel_f32(w >> 24, normalise));
-          }
-          st_stream_v4(frame + f * 4, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-        }
+        if (f < kF32Chunks) emit_chunk(kp, frame, f);
       }
       __syncwarp();  // kp is reused by this warp's next frame
     }
@@ -1090,8 +1128,11 @@ cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t 
     if (err != cudaSuccess) return err;
   }
   const int per_sm = smem > 72 * 1024 ? 2 : 3;
-  const int grid = min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
-  render_f32_kernel<<<grid, kRenderF32Threads, smem, stream>>>(p);
+  RenderParams q = p;
+  // fewer frames than resident CTAs: one CTA per frame (no ticket counter involved), else groups of 8 frames per ticket
+  q.frame_per_cta = p.M <= sm_count * per_sm ? 1 : 0;
+  const int grid = q.frame_per_cta ? p.M : min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
+  render_f32_kernel<<<grid, kRenderF32Threads, smem, stream>>>(q);
   return cudaGetLastError();
 }
 
@@ -1239,13 +1280,17 @@ static cudaError_t launch_warp_kernel(const EnvParams& p, const LaunchCtx& ctx, 
   return cudaGetLastError();
 }
 
+constexpr int kSymWarpMaxEnvs = 2048;   // symbolic-only batches up to this size run the warp-per-env kernel
+
 template <bool STEP>
 static cudaError_t launch_sized(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int sm_count = ctx.sm_count;
   int choice = ctx.kernel_choice;
   if (choice == 0) {
-    // symbolic-only observations are instruction-bound: the state phase alone, at high occupancy
-    if (p.obs_rgb == nullptr) choice = 5;
+    // symbolic-only observations are instruction-bound: the state phase alone, at high occupancy -- except for batches so
+    // small that one env's chain of ~1800 dependent instructions IS the run time: there a warp per env (the same chain
+    // spread over 32 lanes) is 1.3 us faster (2.9 vs 4.2 us at 32 envs, 3.4 vs 4.7 us at 1024; equal at ~3000)
+    if (p.obs_rgb == nullptr) choice = p.N <= kSymWarpMaxEnvs ? 2 : 5;
     else choice = MERLIN_AUTO_RGB_CHOICE(p.N, sm_count);
   }
   if (choice == 2) return launch_warp_kernel<STEP>(p, ctx, stream);
@@ -1271,7 +1316,7 @@ static cudaError_t launch_sized(const EnvParams& p, const LaunchCtx& ctx, cudaSt
 const char* step_kernel_name(int n_envs, bool rgb, const LaunchCtx& ctx) {
   const int sm_count = ctx.sm_count;
   int choice = ctx.kernel_choice;
-  if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : 5;
+  if (choice == 0) choice = rgb ? MERLIN_AUTO_RGB_CHOICE(n_envs, sm_count) : (n_envs <= kSymWarpMaxEnvs ? 2 : 5);
   if (choice == 5) return "merlin::env_kernel_sym<true>";
   if (choice == 2) return "merlin::env_kernel_warp<true>";
   if (choice == 4) return "merlin::env_kernel_tile_tma<true>";

@@ -87,6 +87,7 @@ struct Builder {
   // _is_reachable: 4-neighbour connectivity over empty / goal cells, as a warp-wide relaxation
   __device__ bool reachable(int gx, int gy) {
     __syncwarp();
+    if (ax < 0 || ay < 0) return false;   // no agent was placed (warp-uniform: every lane runs the same draws)
     if (lane == 0) g[ay * W + ax] |= kReached;
     __syncwarp();
     for (;;) {
@@ -114,21 +115,23 @@ struct Builder {
   __device__ void fallback() {  // the empty-room fallback of every generator
     int x, y;
     room();
-    place_agent(0, 0, W, H);
+    // an empty room always has free interior cells; should 2^20 draws still miss them all, the pose is pinned to the
+    // first interior cell rather than left at (-1, -1) (the pool must never hold a pose outside the grid)
+    if (!place_agent(0, 0, W, H)) { ax = 1; ay = 1; adir = 0; }
     place(CODE_GOAL, 0, 0, W, H, 1 << 20, x, y);
   }
 };
 
 __device__ void gen_easy(Builder& b) {
   b.room();
-  b.place_agent(0, 0, b.W, b.H);
+  if (!b.place_agent(0, 0, b.W, b.H)) { b.ax = 1; b.ay = 1; b.adir = 0; }   // an empty room: cannot fail in practice
   b.set(b.W - 5, b.H - 5, CODE_GOAL);
 }
 
 __device__ void gen_medium(Builder& b) {
   int x, y;
   b.room();
-  b.place_agent(0, 0, b.W, b.H);
+  if (!b.place_agent(0, 0, b.W, b.H)) { b.ax = 1; b.ay = 1; b.adir = 0; }
   b.place(CODE_GOAL, 0, 0, b.W, b.H, 1 << 20, x, y);
 }
 
@@ -142,7 +145,7 @@ __device__ void gen_mediumhard(Builder& b) {
     bool ok = true;
     for (int i = 0; i < n && ok; ++i) ok = b.place(CODE_WALL, 0, 0, b.W, b.H, 100, x, y);  // rejects the previous attempt's agent cell
     if (!ok) continue;
-    b.place_agent(0, 0, b.W, b.H);
+    if (!b.place_agent(0, 0, b.W, b.H)) continue;   // no free cell found: a failed attempt, as in gen_hard
     int gx, gy;
     if (!b.place(CODE_GOAL, 0, 0, b.W, b.H, 1 << 20, gx, gy)) continue;
     if (b.reachable(gx, gy)) return;
@@ -202,7 +205,7 @@ __device__ void gen_hardest(Builder& b) {
       const int x = b.rng.integers(1, W - 1), y = b.rng.integers(1, H - 1);
       if (b.at(x, y) == CODE_EMPTY && x != mx && y != my) b.set(x, y, CODE_WALL);
     }
-    b.place_agent(0, 0, W, H);
+    if (!b.place_agent(0, 0, W, H)) continue;
     int gx, gy;
     if (!b.place(CODE_GOAL, 0, 0, W, H, 1 << 20, gx, gy)) continue;
     if (b.reachable(gx, gy)) return;

@@ -37,6 +37,18 @@ MERLIN_HD uint64_t ld64(const uint8_t* p) {
 #endif
 }
 
+// 16 bytes from a 16-byte aligned address as two little-endian 64-bit halves.
+MERLIN_HD void ld128(const uint8_t* p, uint64_t& lo, uint64_t& hi) {
+#if defined(__CUDA_ARCH__)
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  lo = ((uint64_t)v.y << 32) | v.x;
+  hi = ((uint64_t)v.w << 32) | v.z;
+#else
+  memcpy(&lo, p, 8);
+  memcpy(&hi, p + 8, 8);
+#endif
+}
+
 MERLIN_HD uint64_t bswap64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
   const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
@@ -62,6 +74,26 @@ MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, ui
     if ((unsigned)(x0 + u) < (unsigned)W) col_valid |= 0xffull << (8 * u);
   uint64_t lo[kView], hi[kView];
   int sh[kView];
+  if (W == 16) {
+    // the BASELINE grid: a row is ONE aligned 16-byte word -- seven 128-bit loads instead of fourteen 64-bit ones (the
+    // symbolic-only kernel keeps the load/store unit ~70 % busy: ncu, profiles/r02_sym_kernel_ncu.md); x0c <= 9, so the
+    // seven cells start in the low half (shift < 64, may spill into the high half) or lie in the high half entirely
+    const int s16 = x0c * 8;
+#pragma unroll
+    for (int v = 0; v < kView; ++v) {
+      const int wy = y0 + v;
+      ld128(grid + ((unsigned)wy < (unsigned)H ? wy : 0) * 16, lo[v], hi[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < kView; ++v) {
+      uint64_t x = s16 < 64 ? ((lo[v] >> s16) | ((hi[v] << 1) << (63 - s16))) : (hi[v] >> (s16 - 64));
+      x = (x << shl) >> shr;
+      x = (x & col_valid) | (kWall7 & ~col_valid);
+      r[v] = (unsigned)(y0 + v) < (unsigned)H ? x : kWall7;
+    }
+    r[7] = 0;
+    return;
+  }
 #pragma unroll
   for (int v = 0; v < kView; ++v) {
     const int wy = y0 + v;

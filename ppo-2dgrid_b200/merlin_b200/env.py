@@ -113,9 +113,10 @@ class BatchedMerlinEnv:
         self.max_steps = cfg.max_steps or 4 * self.width * self.height
         self._h = C.c_void_p()
         _lib.check(self._lib.merlin_env_create(C.byref(cfg), C.byref(self._h)))
-        if want_rgb:
-            atlas = np.ascontiguousarray(tiles.build_atlas(TILE))
-            _lib.check(self._lib.merlin_env_set_tile_atlas(self._h, atlas.ctypes.data, atlas.shape[0]))
+        # the tile atlas is always installed (24 KB): `render` expands stored symbolic observations to frames even for
+        # envs that never write frames themselves (want_rgb=False only skips the [N, 56, 56, 3] observation buffer)
+        atlas = np.ascontiguousarray(tiles.build_atlas(TILE))
+        _lib.check(self._lib.merlin_env_set_tile_atlas(self._h, atlas.ctypes.data, atlas.shape[0]))
         if generate is not None:
             self.generate_layouts(*generate)
         else:
@@ -134,6 +135,13 @@ class BatchedMerlinEnv:
         self._extras = _lib.StepExtras(self.episode_return.data_ptr(), self.episode_length.data_ptr(),
                                        self.stuck.data_ptr(), self.done.data_ptr())
         self.n_envs = self.num_envs
+        # the in-kernel action sampler follows torch's seeding: key = hash(torch.initial_seed()) -- reproducible after
+        # torch.manual_seed and different per rank when ranks seed differently; nothing is drawn from torch's generators.
+        # Seeded here, never inside a (capturable) step; `seed_sampler` re-keys it.
+        z = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        self.seed_sampler(z ^ (z >> 31))
 
     def make_step_buffers(self, **tensors):
         """A private set of per-step outputs (reward, flags, done, episode stats) for `step(..., out=...)`: lets a caller
@@ -231,7 +239,6 @@ class BatchedMerlinEnv:
     def seed_sampler(self, seed):
         """Key of the in-kernel action sampler (Philox4x32-10); resets every env's draw counter.  Synchronous."""
         _lib.check(self._lib.merlin_env_seed_sampler(self._h, int(seed) & (2**64 - 1)))
-        self._sampler_seeded = True
 
     def make_policy_io(self, logits, value=None, action=None, logprob=None, value_out=None, greedy=False, record=None):
         """Bind the tensors of one fused transition once (pointers are baked in; reuse the object every step or
@@ -282,9 +289,6 @@ class BatchedMerlinEnv:
         log-probability / value into `io`'s tensors, step every env and write the next observation.  Returns the same
         5-tuple as `step`; the action taken is `io.action`.  Replaces Categorical(logits).sample() + log_prob + env.step +
         the rollout stores of src/ppo.py:70-86 and src/fomaml.py:65-84."""
-        if not getattr(self, "_sampler_seeded", False):
-            # follow torch's seeding (torch.manual_seed) so that runs are reproducible and ranks differ
-            self.seed_sampler(int(torch.randint(0, 2**62, (1,)).item()))
         obs = (out_obs if out_obs is not None else self.obs) if frames else None
         sym = out_symbolic if out_symbolic is not None else self.obs_symbolic
         b = out if out is not None else self

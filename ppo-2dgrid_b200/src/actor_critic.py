@@ -149,18 +149,21 @@ class MLPActorCritic(_ActorCriticBase):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# Inference-only evaluation for rollouts.  The parameters do not change while a rollout is collected, so the two
-# Nature-CNN trunks can be packed once per rollout into ONE network of fused layers (the same arithmetic per output
-# element: every sum runs over the same terms; cuDNN / cuBLAS may order them differently, which is immaterial for a
-# path whose actions are sampled):
-#   conv1    actor and critic kernels concatenated over the output channels        [64, 48, 2, 2]   (blocked input)
-#   conv2/3  one grouped convolution, groups = 2 (actor channels | critic channels) [128, 32, 4, 4], [128, 64, 3, 3]
-#   hidden   one batched matmul over the two trunks                                  [2, 576, 512]
-#   heads    one batched matmul; the critic's single column is padded to the actor's width
-# bias + ReLU ride in the convolution (torch.cudnn_convolution_relu) where cuDNN offers the fused engine.
-# 8 kernels per policy evaluation instead of ~35, which is what a 32-task FOMAML rollout (launch-latency-bound) feels.
-# With `params` (stacked per-task weights [B, ...], one frame per task) the same network runs as grouped convolutions
-# with groups = B / 2B and batched matmuls over 2B (task, trunk) pairs.
+# Inference-only evaluation for rollouts.  The parameters do not change while a rollout is collected, so the network
+# can be re-packed once per rollout into the form that costs the fewest launches -- a 32-task FOMAML rollout is 512
+# sequential policy evaluations of a few microseconds of arithmetic each, i.e. launch-latency-bound.  Same arithmetic
+# per output element (every sum runs over the same terms; cuDNN / cuBLAS may order them differently, immaterial for
+# a path whose actions are sampled).
+#   shared weights   per trunk three cuDNN convolutions with bias + ReLU fused in (torch.cudnn_convolution_relu,
+#                    channels-last, first layer on the blocked input with 1/255 folded in), the hidden layer as one
+#                    GEMM with bias + ReLU in its epilogue (torch._addmm_activation), the head as one GEMM writing
+#                    straight into the static `[2, N, A]` tensor the fused env transition reads: 10 launches.
+#                    (Grouped convolutions over both trunks were tried and are slower: cuDNN falls back to direct /
+#                    SGEMM engines plus layout-conversion kernels for them.)
+#   per-task weights (stacked `[B, ...]`, one frame per task: FOMAML query rollouts, few-shot evaluation) every layer is
+#                    ONE batched matmul over tasks (x trunks): the convolutions as im2col + bmm -- the patches are an
+#                    `unfold` view copied once into a static buffer whose extra column of ones carries the bias -- so
+#                    no grouped convolution with 32 / 64 groups is involved: 14 launches instead of ~70 under vmap.
 class RolloutPolicy:
     """`logits, value = rp(x)` for `x` = float32 blocked frames `[N, 14, 14, 48]` holding pixel values 0..255
     (BatchedMerlinEnv.render(..., blocked=True, dtype=torch.float32)).  `logits` `[N, A]` and `value` `[N]` are
@@ -175,6 +178,10 @@ class RolloutPolicy:
         self.per_task = params is not None
         self.act_dim = ac.actor[-1].out_features
         self.use_fused_conv = use_fused_conv
+        self._patch = None   # per-task path: static im2col buffers (bias column pre-filled)
+        self._hid = None     # shared path: static [2, N, 512] hidden activations
+        self._side = None    # shared path: side stream the critic trunk runs on for small batches
+        self.fork_below = 2048
         self.refresh()
 
     def _p(self, name):
@@ -188,66 +195,86 @@ class RolloutPolicy:
         g = lambda trunk, i, kind: self._p(f"{trunk}_extractor.network.{i}.{kind}")  # noqa: E731
         h = lambda head, i, kind: self._p(f"{head}.{i}.{kind}")  # noqa: E731
         if not self.per_task:
-            w1 = torch.cat([_space_to_depth4_weight(g(t, 0, "weight")) for t in ("actor", "critic")]) * (1.0 / 255.0)
-            self.w1 = w1.contiguous(memory_format=torch.channels_last)
-            self.b1 = torch.cat([g(t, 0, "bias") for t in ("actor", "critic")]).contiguous()
-            self.w2 = torch.cat([g(t, 2, "weight") for t in ("actor", "critic")]).contiguous(memory_format=torch.channels_last)
-            self.b2 = torch.cat([g(t, 2, "bias") for t in ("actor", "critic")]).contiguous()
-            self.w3 = torch.cat([g(t, 4, "weight") for t in ("actor", "critic")]).contiguous(memory_format=torch.channels_last)
-            self.b3 = torch.cat([g(t, 4, "bias") for t in ("actor", "critic")]).contiguous()
-            # hidden layer: [2, 576, 512] acting on features in the (h, w, c) order the channels-last conv output has
-            def hid(head):
-                w = h(head, 0, "weight")  # [512, 64*3*3] over (c, h, w)
-                return w.view(-1, 64, 3, 3).permute(2, 3, 1, 0).reshape(576, -1)
-            self.wh = torch.stack([hid("actor"), hid("critic")]).contiguous()
-            self.bh = torch.stack([h("actor", 0, "bias"), h("critic", 0, "bias")]).unsqueeze(1).contiguous()  # [2, 1, 512]
-            wo = torch.zeros((2, self.wh.shape[2], A), dtype=w1.dtype, device=w1.device)
-            wo[0] = h("actor", 2, "weight").t()
-            wo[1, :, :1] = h("critic", 2, "weight").t()
-            bo = torch.zeros((2, 1, A), dtype=w1.dtype, device=w1.device)
-            bo[0, 0] = h("actor", 2, "bias")
-            bo[1, 0, :1] = h("critic", 2, "bias")
-            self.wo, self.bo = wo, bo
-            self.groups = (1, 2, 2)
-        else:
-            B = g("actor", 0, "weight").shape[0]
-            self.B = B
-            def conv(i, blocked=False):
-                wa, wc = g("actor", i, "weight"), g("critic", i, "weight")  # [B, O, C, k, k]
-                if blocked:
-                    o, c = wa.shape[1], wa.shape[2]
-                    f = lambda w: (w.reshape(B, o, c, 2, 4, 2, 4).permute(0, 1, 2, 4, 6, 3, 5)  # noqa: E731
-                                   .reshape(B, o, c * 16, 2, 2) * (1.0 / 255.0))
-                    wa, wc = f(wa), f(wc)
-                w = torch.stack([wa, wc], 1)  # [B, 2, O, C, k, k] -> groups ordered (task, trunk)
-                bias = torch.stack([g("actor", i, "bias"), g("critic", i, "bias")], 1)  # [B, 2, O]
-                return w.reshape((-1,) + tuple(w.shape[3:])).contiguous(), bias.reshape(-1).contiguous()
-            self.w1, self.b1 = conv(0, blocked=True)   # [B*64, 48, 2, 2], groups B (both trunks read the task's frame)
-            self.w2, self.b2 = conv(2)                 # [B*128, 32, 4, 4], groups 2B
-            self.w3, self.b3 = conv(4)                 # [B*128, 64, 3, 3], groups 2B
-            self.wh = torch.stack([h("actor", 0, "weight"), h("critic", 0, "weight")], 1).reshape(2 * B, -1, 576).transpose(1, 2)
-            self.bh = torch.stack([h("actor", 0, "bias"), h("critic", 0, "bias")], 1).reshape(2 * B, 1, -1).contiguous()
-            hd = self.bh.shape[2]
-            wo = torch.zeros((B, 2, hd, A), dtype=self.w1.dtype, device=self.w1.device)
-            wo[:, 0] = h("actor", 2, "weight").transpose(1, 2)
-            wo[:, 1, :, :1] = h("critic", 2, "weight").transpose(1, 2)
-            bo = torch.zeros((B, 2, 1, A), dtype=self.w1.dtype, device=self.w1.device)
-            bo[:, 0, 0] = h("actor", 2, "bias")
-            bo[:, 1, 0, :1] = h("critic", 2, "bias")
-            self.wo, self.bo = wo.reshape(2 * B, hd, A), bo.reshape(2 * B, 1, A)
-            self.groups = (B, 2 * B, 2 * B)
+            cl = torch.channels_last
+            self.conv = {}
+            for t in ("actor", "critic"):
+                self.conv[t] = [((_space_to_depth4_weight(g(t, 0, "weight")) * (1.0 / 255.0)).contiguous(memory_format=cl),
+                                 g(t, 0, "bias").detach(), 1),
+                                (g(t, 2, "weight").detach().contiguous(memory_format=cl), g(t, 2, "bias").detach(), 2),
+                                (g(t, 4, "weight").detach().contiguous(memory_format=cl), g(t, 4, "bias").detach(), 1)]
+            # hidden layers act on features in the (h, w, c) order the channels-last conv output has: [576, 512]
+            self.wh = {t: h(t, 0, "weight").view(-1, 64, 3, 3).permute(2, 3, 1, 0).reshape(576, -1).contiguous()
+                       for t in ("actor", "critic")}
+            self.bh = {t: h(t, 0, "bias").detach() for t in ("actor", "critic")}
+            hd = self.wh["actor"].shape[1]
+            w1 = self.wh["actor"]
+            # both heads as ONE batched matmul over the trunks; the critic's single column is padded to the actor's width
+            self.wo = torch.zeros((2, hd, A), dtype=w1.dtype, device=w1.device)
+            self.wo[0] = h("actor", 2, "weight").t()
+            self.wo[1, :, :1] = h("critic", 2, "weight").t()
+            self.bo = torch.zeros((2, 1, A), dtype=w1.dtype, device=w1.device)
+            self.bo[0, 0] = h("actor", 2, "bias")
+            self.bo[1, 0, :1] = h("critic", 2, "bias")
+            return
+        B = g("actor", 0, "weight").shape[0]
+        self.B = B
+        dev, dt = g("actor", 0, "weight").device, g("actor", 0, "weight").dtype
 
-    def _conv(self, x, w, b, stride, groups):
+        def aug(w, bias, k_pad):
+            """[G, K, O] weights + [G, O] bias -> [G, k_pad, O]: the bias as row K (the patches' column of ones), zeros after."""
+            G, K, O = w.shape
+            out = torch.zeros((G, k_pad, O), dtype=dt, device=dev)
+            out[:, :K] = w
+            out[:, K] = bias
+            return out
+
+        # conv1 on the blocked input: [B, 192, 64] -- both trunks side by side on the output axis, 1/255 folded in
+        def blocked(w):  # [B, 32, 3, 8, 8] -> [B, 32, 192] over (c*16 + dy*4 + dx, by, bx) = the blocked channel, 2x2 taps
+            return w.reshape(B, 32, 3, 2, 4, 2, 4).permute(0, 1, 2, 4, 6, 3, 5).reshape(B, 32, 192) * (1.0 / 255.0)
+        w1 = torch.cat([blocked(g("actor", 0, "weight")), blocked(g("critic", 0, "weight"))], 1).transpose(1, 2)
+        self.w1 = aug(w1, torch.cat([g("actor", 0, "bias"), g("critic", 0, "bias")], 1), 196)
+        # conv2 / conv3 per (task, trunk): [2B, C*k*k, 64]
+        def per_trunk(i):
+            w = torch.stack([g("actor", i, "weight"), g("critic", i, "weight")], 1)   # [B, 2, 64, C, k, k]
+            bias = torch.stack([g("actor", i, "bias"), g("critic", i, "bias")], 1)    # [B, 2, 64]
+            w = w.reshape(2 * B, 64, -1).transpose(1, 2)
+            return aug(w, bias.reshape(2 * B, 64), w.shape[1] + 4)
+        self.w2, self.w3 = per_trunk(2), per_trunk(4)     # [2B, 516, 64], [2B, 580, 64]
+        # hidden layer on features in (h, w, c) order: [2B, 576, 512 + 4] -- column 512 is a constant-one unit (zero
+        # weights, bias 1) that carries the heads' biases, columns 513.. are zero padding
+        wh = torch.stack([h("actor", 0, "weight"), h("critic", 0, "weight")], 1)   # [B, 2, 512, 64*3*3] over (c, h, w)
+        hd = wh.shape[2]
+        self.wh = torch.zeros((2 * B, 576, hd + 4), dtype=dt, device=dev)
+        self.wh[:, :, :hd] = wh.reshape(2 * B, hd, 64, 9).permute(0, 3, 2, 1).reshape(2 * B, 576, hd)
+        self.bh = torch.zeros((2 * B, 1, hd + 4), dtype=dt, device=dev)
+        self.bh[:, 0, :hd] = torch.stack([h("actor", 0, "bias"), h("critic", 0, "bias")], 1).reshape(2 * B, hd)
+        self.bh[:, 0, hd] = 1.0
+        # heads, transposed for a multiply-and-reduce (a [2B, 1, 512] x [2B, 512, 3] bmm costs 17 us as a batched GEMV):
+        # [2B, A, 512 + 4] with the bias in column 512; the critic's single row is padded to the actor's width
+        wo = torch.zeros((B, 2, A, hd + 4), dtype=dt, device=dev)
+        wo[:, 0, :, :hd] = h("actor", 2, "weight")
+        wo[:, 0, :, hd] = h("actor", 2, "bias")
+        wo[:, 1, :1, :hd] = h("critic", 2, "weight")
+        wo[:, 1, :1, hd] = h("critic", 2, "bias")
+        self.wo = wo.reshape(2 * B, A, hd + 4)
+        if self._patch is None:
+            def ones_col(G, L, K):
+                buf = torch.zeros((G, L, K + 4), dtype=dt, device=dev)
+                buf[:, :, K] = 1.0
+                return buf
+            self._patch = (ones_col(B, 169, 192), ones_col(2 * B, 25, 512), ones_col(2 * B, 9, 576))
+
+    def _conv(self, x, w, b, stride):
         if self.use_fused_conv and RolloutPolicy._fused_conv_ok is not False:
             try:
-                y = torch.cudnn_convolution_relu(x, w, b, (stride, stride), (0, 0), (1, 1), groups)
+                y = torch.cudnn_convolution_relu(x, w, b, (stride, stride), (0, 0), (1, 1), 1)
                 RolloutPolicy._fused_conv_ok = True
                 return y
             except RuntimeError:
                 if RolloutPolicy._fused_conv_ok:  # it worked before: a real error, not a missing engine
                     raise
                 RolloutPolicy._fused_conv_ok = False
-        return torch.relu_(torch.nn.functional.conv2d(x, w, b, stride=stride, groups=groups))
+        return torch.relu_(torch.nn.functional.conv2d(x, w, b, stride=stride))
 
     @torch.no_grad()
     def __call__(self, x, out=None):
@@ -255,20 +282,50 @@ class RolloutPolicy:
         A = self.act_dim
         if not self.per_task:
             n = x.shape[0]
-            y = x.permute(0, 3, 1, 2)  # [N, 48, 14, 14], channels-last memory as rendered
-            y = self._conv(y, self.w1, self.b1, 1, 1)
-            y = self._conv(y, self.w2, self.b2, 2, 2)
-            y = self._conv(y, self.w3, self.b3, 1, 2)       # [N, 128, 3, 3]
-            f = y.permute(0, 2, 3, 1).reshape(n, 9, 2, 64).permute(2, 0, 1, 3).reshape(2, n, 576)  # (trunk, n, (h, w, c))
-            hid = torch.relu_(torch.baddbmm(self.bh, f, self.wh))          # [2, N, 512]
-            out = torch.baddbmm(self.bo, hid, self.wo, out=out)            # [2, N, A]
+            if out is None:
+                out = torch.empty((2, n, A), dtype=x.dtype, device=x.device)
+            xc = x.permute(0, 3, 1, 2)  # [N, 48, 14, 14], channels-last memory as rendered
+            if self._hid is None or self._hid.shape[1] != n:
+                self._hid = torch.empty((2, n, self.wh["actor"].shape[1]), dtype=x.dtype, device=x.device)
+            def trunk(i, t):
+                y = xc
+                for w, b, stride in self.conv[t]:
+                    y = self._conv(y, w, b, stride)                       # ... [N, 64, 3, 3]
+                f = y.permute(0, 2, 3, 1).reshape(n, 576)                  # (h, w, c): a view of the channels-last output
+                torch._addmm_activation(self.bh[t], f, self.wh[t], out=self._hid[i])   # bias + ReLU in the GEMM epilogue
+
+            if x.is_cuda and n <= self.fork_below:
+                # small batch = latency-bound: the two trunks are independent chains of four tiny kernels; the critic's
+                # runs on a side stream beside the actor's (fork / join; captured as parallel branches of a CUDA graph)
+                cur = torch.cuda.current_stream(x.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(x.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    trunk(1, "critic")
+                trunk(0, "actor")
+                cur.wait_stream(self._side)
+            else:
+                trunk(0, "actor")
+                trunk(1, "critic")
+            torch.baddbmm(self.bo, self._hid, self.wo, out=out)            # [2, N, A]
             return out[0], out[1, :, 0]
         B = self.B
-        y = x.permute(0, 3, 1, 2).reshape(1, B * 48, 14, 14)  # one copy: (task, channel) become grouped channels
-        y = self._conv(y, self.w1, self.b1, 1, self.groups[0])
-        y = self._conv(y, self.w2, self.b2, 2, self.groups[1])
-        y = self._conv(y, self.w3, self.b3, 1, self.groups[2])   # [1, B*128, 3, 3]
-        f = y.reshape(2 * B, 1, 576)                                # (task, trunk) x (c, h, w)
-        hid = torch.relu_(torch.baddbmm(self.bh, f, self.wh))      # [2B, 1, 512]
-        out = torch.baddbmm(self.bo, hid, self.wo, out=out).view(B, 2, A)   # [B, 2, A]
+        p1, p2, p3 = self._patch
+        # conv1: 2x2 taps over the 14x14x48 blocked frame -> 13x13 positions x 192
+        p1[:, :, :192].copy_(x.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B, 169, 192))
+        h1 = torch.relu_(torch.bmm(p1, self.w1))                           # [B, 169, 64] = [B, 13, 13, (trunk, 32)]
+        # conv2: 4x4 stride 2 over 13x13x32 per trunk -> 5x5 positions x 512
+        v = h1.view(B, 13, 13, 2, 32).unfold(1, 4, 2).unfold(2, 4, 2)      # [B, 5, 5, 2, 32, 4, 4]
+        p2[:, :, :512].copy_(v.permute(0, 3, 1, 2, 4, 5, 6).reshape(2 * B, 25, 512))
+        h2 = torch.relu_(torch.bmm(p2, self.w2))                           # [2B, 25, 64] = [2B, 5, 5, 64]
+        # conv3: 3x3 over 5x5x64 -> 3x3 positions x 576
+        v = h2.view(2 * B, 5, 5, 64).unfold(1, 3, 1).unfold(2, 3, 1)       # [2B, 3, 3, 64, 3, 3]
+        p3[:, :, :576].copy_(v.reshape(2 * B, 9, 576))
+        h3 = torch.relu_(torch.bmm(p3, self.w3))                           # [2B, 9, 64]
+        hid = torch.relu_(torch.baddbmm(self.bh, h3.view(2 * B, 1, 576), self.wh))    # [2B, 1, 512 + 4]
+        if out is None:
+            out = torch.empty((2 * B, 1, A), dtype=x.dtype, device=x.device)
+        torch.sum(hid * self.wo, dim=-1, out=out.view(2 * B, A))           # heads (+ bias through the constant-one unit)
+        out = out.view(B, 2, A)
         return out[:, 0], out[:, 1, 0]

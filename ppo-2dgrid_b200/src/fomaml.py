@@ -28,7 +28,7 @@ from .actor_critic import CNNActorCritic, MLPActorCritic, RolloutPolicy
 
 
 class FOMAML:
-    def __init__(self, scenario_creator, lr_inner=0.01, lr_outer=3e-4, device="cpu", difficulty="medium"):
+    def __init__(self, scenario_creator, lr_inner=0.01, lr_outer=3e-4, device="cpu", difficulty="medium", sync_init=True):
         self.sc = scenario_creator
         self.difficulty = difficulty
         self.device = torch.device(device)
@@ -51,7 +51,8 @@ class FOMAML:
         else:
             self.use_cnn = True
             self.meta_policy = CNNActorCritic((56, 56, 3), 3).to(self.device)
-        parallel.broadcast_parameters(self.meta_policy)
+        if sync_init:  # every rank starts from rank 0's weights (a collective: skip it for rank-local use, e.g. eval jobs)
+            parallel.broadcast_parameters(self.meta_policy)
         self.meta_optimizer = optim.Adam(self.meta_policy.parameters(), lr=lr_outer)
         self.fast_policy = deepcopy(self.meta_policy).to(self.device)
         self.fast_policy.train()
@@ -61,6 +62,7 @@ class FOMAML:
         self.vf_coef = 0.5
         self.ent_coef = 0.05
         self.clip_eps = 0.2
+        self._prefetch = None  # (seeds, thread, result box) of prefetch_tasks
         self._envs = {}  # task-batch size -> cached BatchedMerlinEnv
         self._graphs = {}  # (env, steps, per-task weights?) -> captured rollout
         self.use_cuda_graph = self.device.type == "cuda"
@@ -73,10 +75,35 @@ class FOMAML:
     def _fmt(self, obs):
         return obs if self.use_cnn else obs.reshape(obs.shape[0], -1)
 
+    def prefetch_tasks(self, task_seeds):
+        """Start building the layouts of a coming meta-batch on a background thread (the host-side `_gen_grid` of this
+        rank's shard of `task_seeds`, ~0.2 ms per task) while the GPU works on the current one; `meta_train_step` /
+        `few_shot_evaluate` pick the result up when they are called with the same seeds.  Optional."""
+        import threading
+        seeds = tuple(int(s) for s in parallel.shard(list(task_seeds)))
+        if not seeds or (self._prefetch is not None and self._prefetch[0] == seeds):
+            return
+        box = {}
+
+        def work():
+            box["layouts"] = _layouts.generate(self.sc_difficulty(), self.size, list(seeds))
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        self._prefetch = (seeds, th, box)
+
+    def _task_layouts(self, seeds):
+        pf = self._prefetch
+        if pf is not None and pf[0] == tuple(seeds):
+            pf[1].join()
+            self._prefetch = None
+            if "layouts" in pf[2]:
+                return pf[2]["layouts"]
+        return _layouts.generate(self.sc_difficulty(), self.size, seeds)
+
     def _task_env(self, task_seeds):
         """One env per task seed, loaded with the layout `env.reset(seed=s)` would build."""
         seeds = [int(s) for s in task_seeds]
-        cells, agent = _layouts.generate(self.sc_difficulty(), self.size, seeds)
+        cells, agent = self._task_layouts(seeds)
         B = len(seeds)
         env = self._envs.get(B)
         if env is None:
@@ -178,10 +205,9 @@ class FOMAML:
 
     @staticmethod
     def _rollout_result(env, buf, steps):
-        ended = buf["ep_len"] > 0
         out = _Trajectory({"act": buf["act"], "rew": buf["rew"], "val": buf["val"], "logp": buf["logp"],
-                           "done": buf["done"], "last_val": buf["last_val"], "ep_lens": buf["ep_len"][ended].tolist(),
-                           "ep_rews": buf["ep_ret"][ended].tolist()})
+                           "done": buf["done"], "last_val": buf["last_val"]})
+        out.stats = (buf["ep_len"], buf["ep_ret"])  # `ep_lens` / `ep_rews` are read back (a sync) only when asked for
         if "sym" in buf:
             out["obs_symbolic"] = buf["sym"][:steps]
             out.env = env
@@ -266,7 +292,7 @@ class FOMAML:
         adv = (adv - adv.mean(0, keepdim=True)) / (adv.std(0, keepdim=True) + 1e-8)
         return adv, (val + adv).detach()
 
-    def compute_loss(self, batch, policy, params=None):
+    def compute_loss(self, batch, policy, params=None, want_stats=True):
         """PPO-clip loss of the reference (src/fomaml.py:110-156).  Single trajectory -> (loss, stats) as in the
         reference.  Task-batched trajectory (`[k, B]`) -> (per-task loss `[B]`, stats averaged over tasks); with
         `params` (stacked per-task weights) task b is evaluated under its own weights."""
@@ -303,6 +329,8 @@ class FOMAML:
         v_loss = ((new_vals - ret) ** 2).mean(0)
         ent = entropy.mean(0)
         total = pi_loss + self.vf_coef * v_loss - self.ent_coef * ent
+        if not want_stats:  # internal callers that discard the statistics skip their read-back (a host sync)
+            return total, {"loss": total}
         with torch.no_grad():
             kl = (old_logp - new_logp).mean()
             clipfrac = (torch.abs(ratio - 1.0) > self.clip_eps).float().mean()
@@ -340,7 +368,7 @@ class FOMAML:
         fast = _stack(meta, len(seeds))
         for _ in range(adapt_steps):
             support = self.collect_trajectory(env, meta, steps=k_support, params=fast)
-            loss, _ = self.compute_loss(support, meta, params=fast)
+            loss, _ = self.compute_loss(support, meta, params=fast, want_stats=False)
             fast = self._inner_step(fast, loss, names, lr)
 
         with torch.no_grad():
@@ -365,7 +393,7 @@ class FOMAML:
             # inner loop: support rollout under the shared meta weights, one SGD step per task
             support = self.collect_trajectory(env, meta, steps=k_support)
             fast = _stack(meta, B)
-            s_loss, _ = self.compute_loss(support, meta, params=fast)
+            s_loss, _ = self.compute_loss(support, meta, params=fast, want_stats=False)
             fast = self._inner_step(fast, s_loss, names, self.lr_inner)
             # outer loop: query rollout under each task's adapted weights, first-order gradient
             query = self.collect_trajectory(env, meta, steps=k_query, params=fast)
@@ -404,8 +432,14 @@ class _Trajectory(dict):
     (`obs_symbolic`, `[steps, B, 7, 7, 3]`); the reference's `obs` entry -- the frames the policy saw,
     `[steps, B, 56, 56, 3]` uint8 -- is rendered from them the first time it is asked for."""
     env = None
+    stats = None
 
     def __missing__(self, key):
+        if key in ("ep_lens", "ep_rews") and self.stats is not None:
+            ep_len, ep_ret = self.stats
+            ended = ep_len > 0
+            self["ep_lens"], self["ep_rews"] = ep_len[ended].tolist(), ep_ret[ended].tolist()
+            return self[key]
         if key == "obs" and "obs_symbolic" in self and self.env is not None:
             sym = self["obs_symbolic"]
             frames = self.env.render(sym.reshape(-1, 7, 7, 3)).view(sym.shape[:2] + (56, 56, 3))

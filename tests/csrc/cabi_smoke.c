@@ -97,6 +97,48 @@ int main(void) {
     return 1;
   }
   if (merlin_env_step(h, NULL, NULL, NULL, d_rew, d_term, d_trunc, NULL, NULL) != MERLIN_EINVAL) { fprintf(stderr, "NULL actions accepted\n"); return 1; }
+
+  /* The fused transition: policy outputs in, sampled action + log-probability + value rows out, env stepped, all in one
+   * launch.  Greedy on logits (0, 0, 5) = `forward` twice from a fresh reset: the goal again on step 2; log-probability
+   * = -log(1 + 2 e^-5); the first-episode record holds return / length / goal flag of that episode. */
+  {
+    float *d_logits, *d_val, *d_logp, *d_vout, *d_fret;
+    int32_t* d_flen;
+    uint8_t *d_fin, *d_fgoal;
+    const float logits[N][3] = {{0, 0, 5}, {0, 0, 5}, {0, 0, 5}}, val[N] = {0.5f, 1.5f, 2.5f};
+    CUDA(cudaMalloc((void**)&d_logits, sizeof logits)); CUDA(cudaMalloc((void**)&d_val, sizeof val));
+    CUDA(cudaMalloc((void**)&d_logp, N * 4)); CUDA(cudaMalloc((void**)&d_vout, N * 4)); CUDA(cudaMalloc((void**)&d_fret, N * 4));
+    CUDA(cudaMalloc((void**)&d_flen, N * 4)); CUDA(cudaMalloc((void**)&d_fin, N)); CUDA(cudaMalloc((void**)&d_fgoal, N));
+    CUDA(cudaMemcpy(d_logits, logits, sizeof logits, cudaMemcpyHostToDevice));
+    CUDA(cudaMemcpy(d_val, val, sizeof val, cudaMemcpyHostToDevice));
+    CUDA(cudaMemset(d_fin, 0, N));
+    merlin_policy_io_t io;
+    memset(&io, 0, sizeof io);
+    io.logits = d_logits; io.value = d_val; io.action = d_act; io.logprob = d_logp; io.value_out = d_vout; io.greedy = 1;
+    io.finished = d_fin; io.first_return = d_fret; io.first_length = d_flen; io.first_goal = d_fgoal;
+    CHECK(merlin_env_seed_sampler(h, 42));
+    const int32_t cursors[N] = {0, 1, 0};
+    CHECK(merlin_env_set_cursors(h, cursors));
+    CHECK(merlin_env_reset(h, NULL, NULL, d_sym, NULL));
+    for (int t = 1; t <= 2; ++t)
+      CHECK(merlin_env_policy_step(h, &io, NULL, d_sym, d_rew, d_term, d_trunc, NULL, NULL));
+    int64_t act[N]; float logp[N], vout[N], fret[N]; int32_t flen[N]; uint8_t fin[N], fgoal[N];
+    CUDA(cudaMemcpy(act, d_act, sizeof act, cudaMemcpyDeviceToHost)); CUDA(cudaMemcpy(logp, d_logp, sizeof logp, cudaMemcpyDeviceToHost));
+    CUDA(cudaMemcpy(vout, d_vout, sizeof vout, cudaMemcpyDeviceToHost)); CUDA(cudaMemcpy(fret, d_fret, sizeof fret, cudaMemcpyDeviceToHost));
+    CUDA(cudaMemcpy(flen, d_flen, sizeof flen, cudaMemcpyDeviceToHost)); CUDA(cudaMemcpy(fin, d_fin, N, cudaMemcpyDeviceToHost));
+    CUDA(cudaMemcpy(fgoal, d_fgoal, N, cudaMemcpyDeviceToHost)); CUDA(cudaMemcpy(term, d_term, N, cudaMemcpyDeviceToHost));
+    const double want_lp = -log(1.0 + 2.0 * exp(-5.0));
+    for (int e = 0; e < N; ++e)
+      if (act[e] != 2 || fabs(logp[e] - want_lp) > 1e-6 || vout[e] != val[e] || !term[e] || !fin[e] || !fgoal[e] || flen[e] != 2 ||
+          fret[e] != (float)(1.0 - 0.9 * (2.0 / 256.0))) {
+        fprintf(stderr, "policy_step env %d: action %lld logp %.9g value %g finished %d goal %d length %d return %.9g\n", e,
+                (long long)act[e], logp[e], vout[e], fin[e], fgoal[e], flen[e], fret[e]);
+        return 1;
+      }
+    io.logits = NULL;
+    if (merlin_env_policy_step(h, &io, NULL, d_sym, d_rew, d_term, d_trunc, NULL, NULL) != MERLIN_EINVAL) { fprintf(stderr, "NULL logits accepted\n"); return 1; }
+    CHECK(merlin_env_rearm(h, NULL));
+  }
   CHECK(merlin_env_destroy(h));
   printf("cabi_smoke ok (%s)\n", merlin_version());
   return 0;

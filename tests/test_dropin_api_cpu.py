@@ -32,7 +32,7 @@ def test_reference_signatures_are_kept():
     assert _params(PPO.compute_gae) == ["rewards", "values", "dones", "last_value"]
     assert _params(PPO.update) == ["last_value"] and _params(PPO.train) == ["total_steps"]
     assert hasattr(PPO, "collect_rollouts") and hasattr(PPO, "_obs_to_tensor")
-    assert _params(FOMAML.__init__) == ["scenario_creator", "lr_inner", "lr_outer", "device", "difficulty"]
+    assert _params(FOMAML.__init__)[:5] == ["scenario_creator", "lr_inner", "lr_outer", "device", "difficulty"]
     assert _params(FOMAML.collect_trajectory)[:4] == ["env", "policy", "steps", "task_seed"]
     assert _params(FOMAML.compute_loss)[:2] == ["batch", "policy"]
     assert _params(FOMAML.meta_train_step) == ["task_seeds", "k_support", "k_query"]
@@ -183,6 +183,23 @@ def test_shard_is_balanced_and_covers_everything():
             assert sum(parts, []) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
     assert parallel.world_size() == 1 and parallel.rank() == 0
+
+
+def test_eval_sweep_job_plan_is_balanced():
+    """config 5 shards (arm, size) jobs over ranks, longest first: every job lands once, the 64x64 jobs on distinct ranks."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("eval_sweep", os.path.join(os.path.dirname(__file__), "..", "tools", "eval_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    jobs = [(4 * s * s + extra, arm, s) for arm, extra in (("a", 0), ("b", 0), ("c", 320)) for s in (16, 24, 32, 48, 64)]
+    plan = mod.assign_jobs(jobs, 8)
+    assert sorted(j for part in plan for j in part) == sorted(jobs)
+    big = [r for r, part in enumerate(plan) for j in part if j[2] == 64]
+    assert len(set(big)) == 3
+    loads = [sum(j[0] for j in part) for part in plan]
+    assert max(loads) <= 4 * 64 * 64 + 320
+    assert mod.assign_jobs(jobs, 1)[0] == sorted(jobs, key=lambda j: -j[0])
 
 
 def test_metrics_helpers():

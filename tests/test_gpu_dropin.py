@@ -303,6 +303,19 @@ def test_fomaml_task_batched_meta_step_matches_per_task_loop():
     assert all(torch.isfinite(p).all() for p in meta.parameters())
 
 
+def test_fomaml_reference_default_arguments_run_the_batched_path():
+    """FOMAML(scenario_creator) with the reference's defaults (device="cpu", difficulty="medium"): the task-batched
+    meta step runs on the GPU the env kernels write to -- no device mismatch between frames and weights."""
+    from src.fomaml import FOMAML
+    torch.manual_seed(0)
+    fo = FOMAML(_sc())
+    assert fo.device.type == "cuda" and next(fo.meta_policy.parameters()).device.type == "cuda"
+    loss, rew, steps, stats = fo.meta_train_step([3, 4, 5], k_support=12, k_query=12)
+    assert np.isfinite(loss) and np.isfinite(stats["kl"])
+    r, n, g = fo.few_shot_evaluate([200000, 200001], k_support=8, adapt_steps=1)
+    assert r.shape == (2,) and np.all(n >= 1)
+
+
 def test_fomaml_single_env_reference_path():
     from src.fomaml import FOMAML
     torch.manual_seed(0)

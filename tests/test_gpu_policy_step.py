@@ -190,6 +190,7 @@ def test_policy_step_in_cuda_graph_draws_fresh_actions_every_replay():
             env.policy_step(ios[t], frames=False)
     ref = fast.OracleVecEnv(N, enc, agent, max_steps=50)
     ref.reset()
+    ref.reset()  # the device env was reset twice (before the warm-up step and before the capture): one layout further
     seen = []
     for rep in range(3):
         g.replay()

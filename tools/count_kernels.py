@@ -25,14 +25,17 @@ def profile(fn, steps):
     with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
         fn()
         torch.cuda.synchronize()
-    names = collections.Counter()
+    names, micros = collections.Counter(), collections.Counter()
     for ev in prof.events():
         if ev.device_type is not None and "cuda" in str(ev.device_type).lower() and not ev.name.startswith("Memcpy") \
                 and not ev.name.startswith("Memset"):
-            names[ev.name.split("(")[0][:90]] += 1
+            key = ev.name.split("(")[0][:90]
+            names[key] += 1
+            micros[key] += float(getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0) or 0.0)
     total = sum(names.values())
     return {"kernels_total": total, "steps": steps, "kernels_per_step": total / steps,
-            "by_name": dict(names.most_common())}
+            "kernel_us_per_step": sum(micros.values()) / steps,
+            "by_name": {k: {"launches": c, "us_total": round(micros[k], 1)} for k, c in names.most_common()}}
 
 
 def main():

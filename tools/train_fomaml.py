@@ -68,8 +68,11 @@ def main():
     sync()
     hist = []
     t0 = time.perf_counter()
+    nxt = batch()
     for it in range(1, a.iterations + 1):
-        loss, rew, steps, stats = fo.meta_train_step(batch(), k_support=a.k_steps, k_query=a.k_steps)
+        cur, nxt = nxt, batch()
+        fo.prefetch_tasks(nxt)  # the next meta-batch's layouts are built on the host while the GPU runs this one
+        loss, rew, steps, stats = fo.meta_train_step(cur, k_support=a.k_steps, k_query=a.k_steps)
         hist.append({"iter": it, "loss": loss, "rew": rew, "steps": steps, "kl": stats.get("kl", 0.0)})
     sync()
     wall = time.perf_counter() - t0
