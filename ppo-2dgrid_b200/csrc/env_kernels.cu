@@ -1,7 +1,7 @@
 // env_kernels.cu -- fused MERLIN env kernels for sm_100a.
 //
-// Every kernel does the same work per environment -- step + wrappers + auto-reset (STEP = true) or a masked reset
-// (STEP = false), then gen_obs (+process_vis), the symbolic encode and the RGB frame -- and differs only in how
+// Every kernel does the same work per environment -- step + wrappers + auto-reset (STEP = 1: actions given; STEP = 2:
+// actions drawn in the kernel from the policy's logits, merlin_env_policy_step) or a masked reset (STEP = 0), then gen_obs (+process_vis), the symbolic encode and the RGB frame -- and differs only in how
 // environments are mapped onto the machine.  Two phases:
 //
 //   state phase   step logic, reward shaping, restart, 49-cell window gather, bitmask visibility -> the 49 tile
@@ -35,6 +35,24 @@ __device__ __forceinline__ void st_stream_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Grid loads carry an L2 cache policy: evict-LAST when the grid is an entry of the shared layout pool.  The pool
+// (16 MB at the benchmark's 65 536 layouts) is re-read by every step while 10 GB of frames stream through the same L2
+// between two uses of a line; tagged evict-last it stays resident.  Measured on B200, 1M envs, RGB, 65 536 layouts:
+// 1.484 -> 1.418 ms per step (7.07e8 -> 7.39e8 env-steps/s, +4.6 %); with the 8192-layout pool of round 1 +0.9 %
+// (profiles/r02_pool_evict_last_ab.txt).  Private (mutable) grids -- 256 B per env, no reuse across envs -- keep the
+// normal policy.
+__device__ __forceinline__ uint64_t grid_policy(bool shared_pool) {
+  uint64_t last, normal;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(last));
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(normal));
+  return shared_pool ? last : normal;
+}
+__device__ __forceinline__ uint32_t ld_cell(const uint8_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 constexpr int kWarpKindStride = 64;   // per-warp slot for the 49 tile kinds of one env
 
 // bit `tile` of the 128-bit "present" mask (four device words, read through the read-only path; they live in device
@@ -57,11 +75,12 @@ struct Flags {
   int n_actions;
   bool mutable_grid, stuck_on, explore_on, auto_reset, advance, want_rgb, want_sym;
   bool doors = true;   // set by the kernels that run the row-parallel observation
+  uint64_t pol;        // L2 cache policy of the grid loads (grid_policy)
   __device__ __forceinline__ explicit Flags(const EnvParams& p)
       : n_actions((p.flags & MERLIN_F_SEVEN_ACTIONS) ? 7 : 3), mutable_grid(p.cells != nullptr),
         stuck_on(p.flags & MERLIN_F_STUCK_PENALTY), explore_on(p.flags & MERLIN_F_EXPLORE_BONUS),
         auto_reset(p.flags & MERLIN_F_AUTO_RESET), advance(!(p.flags & MERLIN_F_RESET_SAME)),
-        want_rgb(p.obs_rgb != nullptr), want_sym(p.obs_sym != nullptr) {}
+        want_rgb(p.obs_rgb != nullptr), want_sym(p.obs_sym != nullptr), pol(grid_policy(p.cells == nullptr)) {}
 };
 
 // The action env e takes this step: read from `actions`, or -- policy I/O -- drawn here from the policy's logits
@@ -73,54 +92,46 @@ struct ActionDraw {
   float logp;
   uint32_t draw;
 };
-// The sampling itself is kept OUT of line: the frame kernels' state phase runs under a 128-register cap, and with this
-// code inlined next to it the register allocation of the hot (actions given) path degrades -- measured on B200 at 1M
-// envs: 1461 us per step inlined vs 1435 us without the policy code (profiles/r02_tile_kernel_ab.txt).
-__device__ __noinline__ void draw_action_from_logits(const float* __restrict__ logits, const uint32_t* __restrict__ draws,
-                                                      int n_actions, int stride, uint32_t seed_lo, uint32_t seed_hi, int greedy,
-                                                      int e, ActionDraw* out) {
-  float lg[kMaxActions];
-  const float* row = logits + (size_t)e * stride;
-#pragma unroll
-  for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? row[a] : 0.f;
-  float u = 0.f;
-  uint32_t draw = 0;
-  if (!greedy) {
-    draw = draws[e];
-    u = sampler_uniform(seed_lo, seed_hi, (uint32_t)e, draw);
-  }
-  const PolicySample smp = sample_policy(lg, n_actions, u, greedy != 0);
-  out->action = smp.action;
-  out->logp = smp.logp;
-  out->draw = draw;
-}
+// The step kernels are instantiated three times: STEP = 0 (masked reset), 1 (step, actions given), 2 (step, actions
+// drawn here from the policy's logits).  The policy code exists only in the STEP = 2 instances: compiled into the
+// others -- even behind a uniform branch, even out of line -- it degrades the register allocation of the frame kernels'
+// state phase, which runs under a 128-register cap (B200, 1M envs: 1461 us per step vs 1434 us without it;
+// profiles/r02_tile_kernel_ab.txt).
+template <bool POLICY>
 __device__ __forceinline__ ActionDraw draw_action(const EnvParams& p, int n_actions, int e) {
   ActionDraw d;
   d.logp = 0.f;
   d.draw = 0;
-  if (p.logits == nullptr) {
+  if (!POLICY) {
     d.action = p.actions[e];
     return d;
   }
-  draw_action_from_logits(p.logits, p.draws, n_actions, p.logits_stride, p.seed_lo, p.seed_hi, p.greedy, e, &d);
+  float lg[kMaxActions];
+  const float* row = p.logits + (size_t)e * p.logits_stride;
+#pragma unroll
+  for (int a = 0; a < kMaxActions; ++a) lg[a] = a < n_actions ? row[a] : 0.f;
+  float u = 0.f;
+  if (!p.greedy) {
+    d.draw = p.draws[e];
+    u = sampler_uniform(p.seed_lo, p.seed_hi, (uint32_t)e, d.draw);
+  }
+  const PolicySample smp = sample_policy(lg, n_actions, u, p.greedy != 0);
+  d.action = smp.action;
+  d.logp = smp.logp;
   return d;
 }
-__device__ __noinline__ void commit_action_rows(int64_t* out_action, float* out_logp, float* out_value, const float* value_in,
-                                                int value_stride, uint32_t* draws, int greedy, int e, long long action,
-                                                float logp, uint32_t draw) {
-  if (!greedy) draws[e] = draw + 1u;
-  out_action[e] = action;
-  out_logp[e] = logp;
-  if (out_value) out_value[e] = value_in[(size_t)e * value_stride];
-}
+template <bool POLICY>
 __device__ __forceinline__ void commit_action(const EnvParams& p, int e, const ActionDraw& d) {
-  if (p.logits == nullptr) return;
-  commit_action_rows(p.out_action, p.out_logp, p.out_value, p.value_in, p.value_stride, p.draws, p.greedy, e, d.action,
-                     d.logp, d.draw);
+  if (!POLICY) return;
+  if (!p.greedy) p.draws[e] = d.draw + 1u;
+  p.out_action[e] = d.action;
+  p.out_logp[e] = d.logp;
+  if (p.out_value) p.out_value[e] = p.value_in[(size_t)e * p.value_stride];
 }
 // First-episode record of deterministic evaluation (see EnvParams::rec_finished).
+template <bool POLICY>
 __device__ __forceinline__ void record_first_episode(const EnvParams& p, int e, bool done, bool goal, float ep_ret, int len) {
-  if (p.rec_finished == nullptr || !done || p.rec_finished[e]) return;
+  if (!POLICY || p.rec_finished == nullptr || !done || p.rec_finished[e]) return;
   p.rec_finished[e] = 1;
   p.rec_return[e] = ep_ret;
   p.rec_length[e] = len;
@@ -223,7 +234,7 @@ __device__ __forceinline__ void store_sym_row(uint8_t* row, const uint64_t (&g)[
 // State phase, one env per lane, for the G envs e0 .. e0+G-1 (lanes >= G idle).  Must be called by a full warp.
 // Leaves kinds_s[lane][kKindStride] / sym_s[lane][147] filled for the envs whose bit is set in the returned mask.
 // SWAR = true: the observation is computed on window rows (obs_swar.cuh; needs W >= 7), else cell by cell.
-template <int G, bool STEP, bool SWAR = false>
+template <int G, int STEP, bool SWAR = false>
 __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags& f, int e0, int lane, uint8_t* kinds_s,
                                                 uint8_t* sym_s) {
   const int e = e0 + lane;
@@ -244,9 +255,9 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
       const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
       const int fidx = fy * p.W + fx;
-      const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
-      const ActionDraw act = draw_action(p, f.n_actions, e);
-      commit_action(p, e, act);
+      const uint32_t fwd = inb ? ld_cell(grid + fidx, f.pol) : CODE_WALL;
+      const ActionDraw act = draw_action<STEP == 2>(p, f.n_actions, e);
+      commit_action<STEP == 2>(p, e, act);
       StepResult r = step_logic(s, act.action, f.n_actions, fwd, inb, fidx, p.max_steps);
       if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
       if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
@@ -270,7 +281,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       if (p.out_ep_length) p.out_ep_length[e] = done ? s.step_count : 0;
       if (p.out_stuck) p.out_stuck[e] = stuck ? 1 : 0;
       if (p.out_done) p.out_done[e] = done ? 1.f : 0.f;
-      record_first_episode(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
+      record_first_episode<STEP == 2>(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
       restart = done && f.auto_reset;
     }
   } else {
@@ -329,7 +340,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
     uint8_t* kind = kinds_s + lane * kKindStride;
     if (SWAR) {
       uint64_t g[kView], seen[kView];
-      observe_swar(s, grid, p.W, p.H, g, seen, f.doors);
+      observe_swar(s, grid, p.W, p.H, g, seen, f.doors, f.pol);
       if (f.want_rgb) {
         uint32_t kw[13];
         kind_words(g, s.carry, kw);
@@ -339,7 +350,8 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
       }
       if (f.want_sym) store_sym_row(sym_s + lane * kSymBytes, g, f.doors);
     } else {
-      const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return grid[idx]; }, kind);
+      const uint64_t pol = f.pol;
+      const uint64_t transp = gather_view(s, p.W, p.H, [&](int idx) -> uint32_t { return ld_cell(grid + idx, pol); }, kind);
       const uint64_t vis = visibility(transp);
       uint8_t* sym = sym_s + lane * kSymBytes;
 #pragma unroll
@@ -367,7 +379,7 @@ __device__ __forceinline__ unsigned state_phase(const EnvParams& p, const Flags&
 
 // ---------------------------------------------------------------------------------------------------
 // env_kernel<G, STEP>: a warp owns G consecutive envs.
-template <int G, bool STEP>
+template <int G, int STEP>
 __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -414,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_kernel(const EnvParams p, con
 //   G=8, 256 x 2  1.034    G=16, 256 x 2  1.024    G=16, 128 x 4  1.021    G=4, 128 x 4  0.920
 // i.e. in-order hand-out lifts the group mapping from 0.92 (static assignment) to 1.05, but more concurrent state phases
 // buy nothing over the tile kernel: its limit is the store stream, not the state-phase chain.  Kept selectable (choice 6).
-template <int G, bool STEP, int THREADS, int MINB, bool SWAR = false>
+template <int G, int STEP, int THREADS, int MINB, bool SWAR = false>
 __global__ void __launch_bounds__(THREADS, MINB) env_kernel_ordered(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -481,7 +493,7 @@ __host__ __device__ constexpr int tile_smem_bytes(int T) {
   return kAtlasBytes + ((T * kKindStride + T * kSymBytes + 15) & ~15) + 16;
 }
 
-template <int T, bool STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm, bool SWAR = false>
+template <int T, int STEP, int THREADS = kTileThreads, int MINB = kTileCtasPerSm, bool SWAR = false>
 __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile(const EnvParams p, const int n_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -582,7 +594,7 @@ __host__ __device__ constexpr int tile_tma_smem_bytes(int T, int threads, int nb
   return tile_smem_bytes(T) + (threads / 32) * nbuf * kImgBytes;
 }
 
-template <int T, bool STEP, int THREADS, int MINB, int NBUF>
+template <int T, int STEP, int THREADS, int MINB, int NBUF>
 __global__ void __launch_bounds__(THREADS, MINB) env_kernel_tile_tma(const EnvParams p, const int n_tiles) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -653,7 +665,7 @@ __host__ __device__ constexpr int sym_kernel_warp_smem(bool swar) {
 #ifndef MERLIN_SYM_MINB
 #define MERLIN_SYM_MINB 10  // 48 registers, 40 warps/SM: 1.16e10 env-steps/s at 1M envs (unconstrained, 56 registers: 1.11e10; 12 CTAs, 40 registers + spills: 1.04e10)
 #endif
-template <bool STEP, bool SWAR = false>
+template <int STEP, bool SWAR = false>
 __global__ void __launch_bounds__(128, SWAR ? MERLIN_SYM_MINB : 1) env_kernel_sym(const EnvParams p, const int n_groups) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -686,7 +698,7 @@ static bool use_swar(const EnvParams& p, const LaunchCtx& ctx, bool frame_kernel
   return ctx.observation_path == 2 || !frame_kernel;
 }
 
-template <bool STEP>
+template <int STEP>
 static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int threads = 128, warps = threads / 32;
   const int n_groups = (p.N + 31) / 32;
@@ -722,7 +734,7 @@ constexpr int kWarpKernelThreads = MERLIN_WARP_THREADS;
 constexpr int kWarpKindBytes = 128;          // 49 premultiplied kinds (u16) per warp, padded
 constexpr int kPairChunks = 2 * kUnitsPerRow / 2;   // 21 16-byte chunks per pair of pixel rows
 
-template <bool STEP>
+template <int STEP>
 __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kernel_warp(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -738,7 +750,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
   long long act_next = 0;
   if (e < p.N) {
     st_next = p.state[e];
-    if (STEP && p.logits == nullptr) act_next = p.actions[e];
+    if (STEP == 1) act_next = p.actions[e];
   }
   if (f.want_rgb) {
     // thread t tests tile t / 2 and copies half of it (6 int4); a 128-thread CTA takes two rounds
@@ -777,7 +789,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
       const int en = e + gridDim.x * warps_per_cta;   // prefetch the next env of this warp
       if (en < p.N) {
         st_next = p.state[en];
-        if (STEP && p.logits == nullptr) act_next = p.actions[en];
+        if (STEP == 1) act_next = p.actions[en];
       }
     }
     unpack_state(st.x, st.y, st.z, st.w, s);
@@ -790,9 +802,9 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
       const int fx = s.x + dir_dx(s.dir), fy = s.y + dir_dy(s.dir);
       const bool inb = (unsigned)fx < (unsigned)p.W && (unsigned)fy < (unsigned)p.H;
       const int fidx = fy * p.W + fx;
-      const uint32_t fwd = inb ? grid[fidx] : CODE_WALL;
+      const uint32_t fwd = inb ? ld_cell(grid + fidx, f.pol) : CODE_WALL;
       ActionDraw act;
-      if (p.logits != nullptr) act = draw_action(p, f.n_actions, e);
+      if (STEP == 2) act = draw_action<true>(p, f.n_actions, e);
       else { act.action = act_in; act.logp = 0.f; act.draw = 0; }
       StepResult r = step_logic(s, act.action, f.n_actions, fwd, inb, fidx, p.max_steps);
       uint32_t vword = 0;
@@ -808,8 +820,8 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
       const bool done = r.terminated || r.truncated;
       __syncwarp();  // every lane has read the old grid cell / visited word / draw counter before lane 0 overwrites them
       if (lane == 0) {
-        commit_action(p, e, act);
-        record_first_episode(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
+        commit_action<STEP == 2>(p, e, act);
+        record_first_episode<STEP == 2>(p, e, done, r.terminated && r.reward > 0.0, ep_ret, s.step_count);
         if (r.bad_action) atomicAdd(p.bad_actions, 1ull);
         if (r.write_idx >= 0 && f.mutable_grid) p.cells[(size_t)e * p.cell_stride + r.write_idx] = (uint8_t)r.write_code;
         if (f.explore_on && vword != vword_in) *vptr = vword;
@@ -865,11 +877,11 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
     uint32_t code0, code1 = CODE_WALL;
     {
       const int wx = s.x + a0 * fx + b0 * rx, wy = s.y + a0 * fy + b0 * ry;
-      code0 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
+      code0 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? ld_cell(grid + wy * p.W + wx, f.pol) : CODE_WALL;
     }
     if (c1 < kCells) {
       const int wx = s.x + a1 * fx + b1 * rx, wy = s.y + a1 * fy + b1 * ry;
-      code1 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? grid[wy * p.W + wx] : CODE_WALL;
+      code1 = ((unsigned)wx < (unsigned)p.W && (unsigned)wy < (unsigned)p.H) ? ld_cell(grid + wy * p.W + wx, f.pol) : CODE_WALL;
     }
     const unsigned t0 = __ballot_sync(0xffffffffu, !((M_OPAQUE >> (code0 & 0xf)) & 1u));
     const unsigned t1 = __ballot_sync(0xffffffffu, c1 < kCells && !((M_OPAQUE >> (code1 & 0xf)) & 1u));
@@ -1181,15 +1193,15 @@ static cudaError_t resident_ctas(Kernel kernel, int threads, size_t smem, int& b
 }
 
 // occupancy-cache slots (LaunchCtx::occ): one per kernel instance
-enum : int { kSlotGroup = 0 /* +2*log2(32/G) + STEP: 8 */, kSlotTile = 8 /* + (T==8)*4 + SWAR*2 + STEP: 8 */,
-             kSlotOrdered = 16 /* + SWAR*2 + STEP: 4 */, kSlotTma = 20 /* + STEP: 2 */, kSlotWarp = 22 /* + STEP: 2 */ };
-static_assert(kSlotWarp + 2 <= kOccSlots, "occupancy cache too small");
+enum : int { kSlotGroup = 0 /* + 3*log2(32/G) + STEP: 12 */, kSlotTile = 12 /* + (T==8)*6 + SWAR*3 + STEP: 12 */,
+             kSlotOrdered = 24 /* + SWAR*3 + STEP: 6 */, kSlotTma = 30 /* + STEP: 3 */, kSlotWarp = 33 /* + STEP: 3 */ };
+static_assert(kSlotWarp + 3 <= kOccSlots, "occupancy cache too small");
 
-template <int G, bool STEP>
+template <int G, int STEP>
 static cudaError_t launch_group_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_groups = (p.N + G - 1) / G;
   const size_t smem = cta_smem_bytes(G);
-  int& blocks_per_sm = ctx.occ[kSlotGroup + 2 * (G == 32 ? 0 : G == 16 ? 1 : G == 8 ? 2 : 3) + (STEP ? 1 : 0)];
+  int& blocks_per_sm = ctx.occ[kSlotGroup + 3 * (G == 32 ? 0 : G == 16 ? 1 : G == 8 ? 2 : 3) + STEP];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel<G, STEP>, kThreads, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
@@ -1199,11 +1211,11 @@ static cudaError_t launch_group_kernel(const EnvParams& p, const LaunchCtx& ctx,
   return cudaGetLastError();
 }
 
-template <int T, bool STEP, bool SWAR, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
+template <int T, int STEP, bool SWAR, int THREADS = kTileThreads, int MINB = kTileCtasPerSm>
 static cudaError_t launch_tile_kernel_impl(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_smem_bytes(T);
-  int& blocks_per_sm = ctx.occ[kSlotTile + (T == 8 ? 4 : 0) + (SWAR ? 2 : 0) + (STEP ? 1 : 0)];
+  int& blocks_per_sm = ctx.occ[kSlotTile + (T == 8 ? 6 : 0) + (SWAR ? 3 : 0) + STEP];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_tile<T, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
@@ -1213,7 +1225,7 @@ static cudaError_t launch_tile_kernel_impl(const EnvParams& p, const LaunchCtx& 
   env_kernel_tile<T, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_tiles);
   return cudaGetLastError();
 }
-template <int T, bool STEP>
+template <int T, int STEP>
 static cudaError_t launch_tile_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   return use_swar(p, ctx, true) ? launch_tile_kernel_impl<T, STEP, true>(p, ctx, stream)
                                 : launch_tile_kernel_impl<T, STEP, false>(p, ctx, stream);
@@ -1224,12 +1236,12 @@ static cudaError_t launch_tile_kernel(const EnvParams& p, const LaunchCtx& ctx, 
 #define MERLIN_ORD_THREADS 128
 #define MERLIN_ORD_CTAS 3
 #endif
-template <int G, bool STEP, bool SWAR, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
+template <int G, int STEP, bool SWAR, int THREADS = MERLIN_ORD_THREADS, int MINB = MERLIN_ORD_CTAS>
 static cudaError_t launch_ordered_kernel_impl(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int warps = THREADS / 32;
   const int n_groups = (p.N + G - 1) / G;
   const size_t smem = kAtlasBytes + warps * warp_smem_bytes(G);
-  int& blocks_per_sm = ctx.occ[kSlotOrdered + (SWAR ? 2 : 0) + (STEP ? 1 : 0)];
+  int& blocks_per_sm = ctx.occ[kSlotOrdered + (SWAR ? 3 : 0) + STEP];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_ordered<G, STEP, THREADS, MINB, SWAR>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
@@ -1239,7 +1251,7 @@ static cudaError_t launch_ordered_kernel_impl(const EnvParams& p, const LaunchCt
   env_kernel_ordered<G, STEP, THREADS, MINB, SWAR><<<grid, THREADS, smem, stream>>>(p, n_groups);
   return cudaGetLastError();
 }
-template <int G, bool STEP>
+template <int G, int STEP>
 static cudaError_t launch_ordered_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   return use_swar(p, ctx, true) ? launch_ordered_kernel_impl<G, STEP, true>(p, ctx, stream)
                                 : launch_ordered_kernel_impl<G, STEP, false>(p, ctx, stream);
@@ -1251,11 +1263,11 @@ static cudaError_t launch_ordered_kernel(const EnvParams& p, const LaunchCtx& ct
 #define MERLIN_TMA_CTAS 3
 #define MERLIN_TMA_NBUF 1
 #endif
-template <int T, bool STEP, int THREADS = MERLIN_TMA_THREADS, int MINB = MERLIN_TMA_CTAS, int NBUF = MERLIN_TMA_NBUF>
+template <int T, int STEP, int THREADS = MERLIN_TMA_THREADS, int MINB = MERLIN_TMA_CTAS, int NBUF = MERLIN_TMA_NBUF>
 static cudaError_t launch_tile_tma_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int n_tiles = (p.N + T - 1) / T;
   const size_t smem = tile_tma_smem_bytes(T, THREADS, NBUF);
-  int& blocks_per_sm = ctx.occ[kSlotTma + (STEP ? 1 : 0)];
+  int& blocks_per_sm = ctx.occ[kSlotTma + STEP];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_tile_tma<T, STEP, THREADS, MINB, NBUF>, THREADS, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
@@ -1266,11 +1278,11 @@ static cudaError_t launch_tile_tma_kernel(const EnvParams& p, const LaunchCtx& c
   return cudaGetLastError();
 }
 
-template <bool STEP>
+template <int STEP>
 static cudaError_t launch_warp_kernel(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   constexpr int warps = kWarpKernelThreads / 32;
   const size_t smem = kAtlasBytes + warps * kWarpKindBytes;
-  int& blocks_per_sm = ctx.occ[kSlotWarp + (STEP ? 1 : 0)];
+  int& blocks_per_sm = ctx.occ[kSlotWarp + STEP];
   if (!blocks_per_sm) {
     cudaError_t err = resident_ctas(env_kernel_warp<STEP>, kWarpKernelThreads, smem, blocks_per_sm);
     if (err != cudaSuccess) return err;
@@ -1282,7 +1294,7 @@ static cudaError_t launch_warp_kernel(const EnvParams& p, const LaunchCtx& ctx, 
 
 constexpr int kSymWarpMaxEnvs = 2048;   // symbolic-only batches up to this size run the warp-per-env kernel
 
-template <bool STEP>
+template <int STEP>
 static cudaError_t launch_sized(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
   const int sm_count = ctx.sm_count;
   int choice = ctx.kernel_choice;
@@ -1331,10 +1343,10 @@ const char* step_kernel_name(int n_envs, bool rgb, const LaunchCtx& ctx) {
 }
 
 cudaError_t launch_env_step(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
-  return launch_sized<true>(p, ctx, stream);
+  return p.logits != nullptr ? launch_sized<2>(p, ctx, stream) : launch_sized<1>(p, ctx, stream);
 }
 cudaError_t launch_env_reset(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream) {
-  return launch_sized<false>(p, ctx, stream);
+  return launch_sized<0>(p, ctx, stream);
 }
 
 }  // namespace merlin

@@ -74,7 +74,7 @@ struct EnvParams {
 
 // Per-handle launch context: kernel choice, observation path and the occupancy cache live in the handle (a process may
 // hold several handles on several devices, driven from different threads).
-constexpr int kOccSlots = 32;
+constexpr int kOccSlots = 40;
 struct LaunchCtx {
   int sm_count;
   int kernel_choice;      // 0 = automatic, 1..6 as merlin_set_kernel_choice

@@ -27,10 +27,15 @@ constexpr uint64_t kB01 = 0x0101010101010101ull;
 constexpr uint64_t kLow7 = 0x00ffffffffffffffull;                 // bytes 0..6
 constexpr uint64_t kWall7 = (kB01 * CODE_WALL) & kLow7;
 
-MERLIN_HD uint64_t ld64(const uint8_t* p) {
+// Grid loads carry an L2 cache policy on the device (`pol`, from grid_policy() in env_kernels.cu: evict-last for the
+// shared layout pool, which every step re-reads while gigabytes of observations stream through the same L2).
+MERLIN_HD uint64_t ld64(const uint8_t* p, uint64_t pol = 0) {
 #if defined(__CUDA_ARCH__)
-  return *reinterpret_cast<const uint64_t*>(p);  // callers pass 8-byte aligned addresses
+  uint64_t v;  // callers pass 8-byte aligned addresses
+  asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
 #else
+  (void)pol;
   uint64_t v;
   memcpy(&v, p, 8);
   return v;
@@ -38,12 +43,11 @@ MERLIN_HD uint64_t ld64(const uint8_t* p) {
 }
 
 // 16 bytes from a 16-byte aligned address as two little-endian 64-bit halves.
-MERLIN_HD void ld128(const uint8_t* p, uint64_t& lo, uint64_t& hi) {
+MERLIN_HD void ld128(const uint8_t* p, uint64_t& lo, uint64_t& hi, uint64_t pol = 0) {
 #if defined(__CUDA_ARCH__)
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  lo = ((uint64_t)v.y << 32) | v.x;
-  hi = ((uint64_t)v.w << 32) | v.z;
+  asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(lo), "=l"(hi) : "l"(p), "l"(pol));
 #else
+  (void)pol;
   memcpy(&lo, p, 8);
   memcpy(&hi, p + 8, 8);
 #endif
@@ -64,7 +68,7 @@ MERLIN_HD uint64_t bswap64(uint64_t x) {
 // branch, so they are in flight together -- with the loads behind per-row branches a lone warp pays one L2 round trip
 // per row.  Every address lies inside [0, cell_stride) of this grid: a row outside the grid reads row 0 instead and is
 // replaced by walls afterwards, and the second word ends at most at the next multiple of 8 after the row's last cell.
-MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, uint64_t (&r)[8]) {
+MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, uint64_t (&r)[8], uint64_t pol = 0) {
   const int x0c = x0 < 0 ? 0 : (x0 > W - kView ? W - kView : x0);
   const int d = x0c - x0;                        // > 0: the window starts left of the grid, < 0: it ends right of it
   const int shl = d > 0 ? 8 * d : 0, shr = d < 0 ? -8 * d : 0;
@@ -82,7 +86,7 @@ MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, ui
 #pragma unroll
     for (int v = 0; v < kView; ++v) {
       const int wy = y0 + v;
-      ld128(grid + ((unsigned)wy < (unsigned)H ? wy : 0) * 16, lo[v], hi[v]);
+      ld128(grid + ((unsigned)wy < (unsigned)H ? wy : 0) * 16, lo[v], hi[v], pol);
     }
 #pragma unroll
     for (int v = 0; v < kView; ++v) {
@@ -100,8 +104,8 @@ MERLIN_HD void window_rows(const uint8_t* grid, int W, int H, int x0, int y0, ui
     const int base = ((unsigned)wy < (unsigned)H ? wy : 0) * W + x0c;
     const int a0 = base & ~7;
     sh[v] = (base & 7) * 8;
-    lo[v] = ld64(grid + a0);
-    hi[v] = ld64(grid + (sh[v] > 8 ? a0 + 8 : a0));
+    lo[v] = ld64(grid + a0, pol);
+    hi[v] = ld64(grid + (sh[v] > 8 ? a0 + 8 : a0), pol);
   }
 #pragma unroll
   for (int v = 0; v < kView; ++v) {
@@ -167,12 +171,12 @@ MERLIN_HD uint64_t visibility8(uint64_t transp) {
 // `doors` = false promises that no cell of the grid is a closed / locked door (walls are then the only opaque cells):
 // one byte-parallel type test per group instead of three.
 MERLIN_HD void observe_swar(const EnvState& s, const uint8_t* grid, int W, int H, uint64_t (&g)[kView],
-                            uint64_t (&seen)[kView], bool doors = true) {
+                            uint64_t (&seen)[kView], bool doors = true, uint64_t pol = 0) {
   // window origin: get_view_exts
   const int x0 = s.dir == 0 ? s.x : (s.dir == 2 ? s.x - (kView - 1) : s.x - kView / 2);
   const int y0 = s.dir == 1 ? s.y : (s.dir == 3 ? s.y - (kView - 1) : s.y - kView / 2);
   uint64_t r[8];
-  window_rows(grid, W, H, x0, y0, r);
+  window_rows(grid, W, H, x0, y0, r, pol);
   // orientation: view (vi, vj) = window (u, v) with   dir 0: (6 - vj, vi)   dir 1: (6 - vi, 6 - vj)
   //                                                   dir 2: (vj, 6 - vi)   dir 3: (vi, vj)
   // i.e. g[vi] = rows (even dir) or columns (odd dir), bytes reversed for dir 0 / 1, index reversed for dir 1 / 2.

@@ -1,18 +1,11 @@
 # development aid (round 2): A/B runs behind profiles/r02_*_ab.txt
 V=ppo-2dgrid_b200/lib/variants
-sw() { python tools/sweep.py --compact --steps 256 "$@" 2>&1 | grep N=; }
-echo "== tile kernel 1M rgb: r01 / current (x2)"
-python .ab/r01/tools/sweep.py --compact --steps 256 --sizes 1048576 --modes rgb 2>&1 | grep N=
-sw --sizes 1048576 --modes rgb,symbolic
-python .ab/r01/tools/sweep.py --compact --steps 256 --sizes 1048576 --modes rgb 2>&1 | grep N=
-sw --sizes 1048576 --modes rgb,symbolic
-echo "== small batches (auto choice)"
-sw --sizes 32,1024,2048,4096,16384 --modes rgb,symbolic
-echo "== fill floor"
-python tools/fill_floor.py 2>&1 | grep N=
-echo "== fomaml"
-python tools/profile_fomaml.py 2>&1 | tail -1
-python tools/count_kernels.py --out gpurun_out/r02_kernels_per_step_after.json > gpurun_out/ck5.log 2>&1
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_policy_step.py -q -m gpu -x 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; tail -3 gpurun_out/bench_b.err
+b() { python bench.py --steps 40 --warmup 5 --skip-learners --skip-cpu-baseline --skip-e2e "$@" 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('   value %.4e  ms/step %.4f  frac %.3f  restarted %d' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['config']['envs_restarted_on_a_new_layout_in_timed_region_rank0']))"; }
+echo "== bench env-steps: layout pool 65536 (default) vs 8192; plain vs evict_last pool loads"
+for i in 1 2; do
+echo "L=65536 plain"; b
+echo "L=65536 evict_last"; MERLIN_B200_LIB=$PWD/$V/lib_evict_last.so b
+echo "L=8192 plain"; b --layouts 8192
+echo "L=8192 evict_last"; MERLIN_B200_LIB=$PWD/$V/lib_evict_last.so b --layouts 8192
+done
 echo done
