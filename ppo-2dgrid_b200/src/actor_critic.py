@@ -173,9 +173,12 @@ class RolloutPolicy:
 
     _fused_conv_ok = None  # probed once per process: does cuDNN run the fused conv+bias+ReLU for these shapes?
 
-    def __init__(self, ac, params=None, use_fused_conv=True):
+    def __init__(self, ac, params=None, use_fused_conv=True, actor_only=False):
         self.ac, self.params = ac, params
         self.per_task = params is not None
+        # actor_only (per-task weights): greedy evaluation needs no value -- the critic trunk's half of every batched
+        # matmul (and of the per-task weight traffic, ~150 MB per step at 100 tasks) is skipped; `value` is then None
+        self.trunks = ("actor",) if (actor_only and self.per_task) else ("actor", "critic")
         self.act_dim = ac.actor[-1].out_features
         self.use_fused_conv = use_fused_conv
         self._patch = None   # per-task path: static im2col buffers (bias column pre-filled)
@@ -202,22 +205,29 @@ class RolloutPolicy:
                                  g(t, 0, "bias").detach(), 1),
                                 (g(t, 2, "weight").detach().contiguous(memory_format=cl), g(t, 2, "bias").detach(), 2),
                                 (g(t, 4, "weight").detach().contiguous(memory_format=cl), g(t, 4, "bias").detach(), 1)]
-            # hidden layers act on features in the (h, w, c) order the channels-last conv output has: [576, 512]
-            self.wh = {t: h(t, 0, "weight").view(-1, 64, 3, 3).permute(2, 3, 1, 0).reshape(576, -1).contiguous()
-                       for t in ("actor", "critic")}
-            self.bh = {t: h(t, 0, "bias").detach() for t in ("actor", "critic")}
-            hd = self.wh["actor"].shape[1]
-            w1 = self.wh["actor"]
-            # both heads as ONE batched matmul over the trunks; the critic's single column is padded to the actor's width
-            self.wo = torch.zeros((2, hd, A), dtype=w1.dtype, device=w1.device)
-            self.wo[0] = h("actor", 2, "weight").t()
-            self.wo[1, :, :1] = h("critic", 2, "weight").t()
-            self.bo = torch.zeros((2, 1, A), dtype=w1.dtype, device=w1.device)
-            self.bo[0, 0] = h("actor", 2, "bias")
-            self.bo[1, 0, :1] = h("critic", 2, "bias")
+            # hidden layers act on features in the (h, w, c) order the channels-last conv output has: [576, 512 + 8] --
+            # unit 512 is a constant one (zero weights, bias 1: ReLU keeps it) that carries the heads' biases, 513.. are padding
+            hd = h("actor", 0, "weight").shape[0]
+            dev, dt = h("actor", 0, "weight").device, h("actor", 0, "weight").dtype
+            self.wh, self.bh = {}, {}
+            for t in ("actor", "critic"):
+                w = torch.zeros((576, hd + 8), dtype=dt, device=dev)
+                w[:, :hd] = h(t, 0, "weight").view(-1, 64, 3, 3).permute(2, 3, 1, 0).reshape(576, hd)
+                bias = torch.zeros(hd + 8, dtype=dt, device=dev)
+                bias[:hd] = h(t, 0, "bias")
+                bias[hd] = 1.0
+                self.wh[t], self.bh[t] = w, bias
+            # both heads over the trunks at once, bias in row 512; the critic's single column is padded to the actor's width
+            self.wo = torch.zeros((2, hd + 8, A), dtype=dt, device=dev)          # for a batched matmul
+            self.wo[0, :hd] = h("actor", 2, "weight").t()
+            self.wo[0, hd] = h("actor", 2, "bias")
+            self.wo[1, :hd, :1] = h("critic", 2, "weight").t()
+            self.wo[1, hd, :1] = h("critic", 2, "bias")
+            self.wo_t = self.wo.transpose(1, 2).contiguous().unsqueeze(1)       # [2, 1, A, 520] for multiply-and-reduce
             return
         B = g("actor", 0, "weight").shape[0]
         self.B = B
+        tr, T = self.trunks, len(self.trunks)
         dev, dt = g("actor", 0, "weight").device, g("actor", 0, "weight").dtype
 
         def aug(w, bias, k_pad):
@@ -228,41 +238,42 @@ class RolloutPolicy:
             out[:, K] = bias
             return out
 
-        # conv1 on the blocked input: [B, 192, 64] -- both trunks side by side on the output axis, 1/255 folded in
+        # conv1 on the blocked input: [B, 192, 32 T] -- the trunks side by side on the output axis, 1/255 folded in
         def blocked(w):  # [B, 32, 3, 8, 8] -> [B, 32, 192] over (c*16 + dy*4 + dx, by, bx) = the blocked channel, 2x2 taps
             return w.reshape(B, 32, 3, 2, 4, 2, 4).permute(0, 1, 2, 4, 6, 3, 5).reshape(B, 32, 192) * (1.0 / 255.0)
-        w1 = torch.cat([blocked(g("actor", 0, "weight")), blocked(g("critic", 0, "weight"))], 1).transpose(1, 2)
-        self.w1 = aug(w1, torch.cat([g("actor", 0, "bias"), g("critic", 0, "bias")], 1), 196)
-        # conv2 / conv3 per (task, trunk): [2B, C*k*k, 64]
+        w1 = torch.cat([blocked(g(t, 0, "weight")) for t in tr], 1).transpose(1, 2)
+        self.w1 = aug(w1, torch.cat([g(t, 0, "bias") for t in tr], 1), 196)
+        # conv2 / conv3 per (task, trunk): [T B, C*k*k, 64]
         def per_trunk(i):
-            w = torch.stack([g("actor", i, "weight"), g("critic", i, "weight")], 1)   # [B, 2, 64, C, k, k]
-            bias = torch.stack([g("actor", i, "bias"), g("critic", i, "bias")], 1)    # [B, 2, 64]
-            w = w.reshape(2 * B, 64, -1).transpose(1, 2)
-            return aug(w, bias.reshape(2 * B, 64), w.shape[1] + 4)
-        self.w2, self.w3 = per_trunk(2), per_trunk(4)     # [2B, 516, 64], [2B, 580, 64]
-        # hidden layer on features in (h, w, c) order: [2B, 576, 512 + 4] -- column 512 is a constant-one unit (zero
+            w = torch.stack([g(t, i, "weight") for t in tr], 1)   # [B, T, 64, C, k, k]
+            bias = torch.stack([g(t, i, "bias") for t in tr], 1)    # [B, T, 64]
+            w = w.reshape(T * B, 64, -1).transpose(1, 2)
+            return aug(w, bias.reshape(T * B, 64), w.shape[1] + 4)
+        self.w2, self.w3 = per_trunk(2), per_trunk(4)     # [T B, 516, 64], [T B, 580, 64]
+        # hidden layer on features in (h, w, c) order: [T B, 576, 512 + 4] -- column 512 is a constant-one unit (zero
         # weights, bias 1) that carries the heads' biases, columns 513.. are zero padding
-        wh = torch.stack([h("actor", 0, "weight"), h("critic", 0, "weight")], 1)   # [B, 2, 512, 64*3*3] over (c, h, w)
+        wh = torch.stack([h(t, 0, "weight") for t in tr], 1)   # [B, T, 512, 64*3*3] over (c, h, w)
         hd = wh.shape[2]
-        self.wh = torch.zeros((2 * B, 576, hd + 4), dtype=dt, device=dev)
-        self.wh[:, :, :hd] = wh.reshape(2 * B, hd, 64, 9).permute(0, 3, 2, 1).reshape(2 * B, 576, hd)
-        self.bh = torch.zeros((2 * B, 1, hd + 4), dtype=dt, device=dev)
-        self.bh[:, 0, :hd] = torch.stack([h("actor", 0, "bias"), h("critic", 0, "bias")], 1).reshape(2 * B, hd)
+        self.wh = torch.zeros((T * B, 576, hd + 4), dtype=dt, device=dev)
+        self.wh[:, :, :hd] = wh.reshape(T * B, hd, 64, 9).permute(0, 3, 2, 1).reshape(T * B, 576, hd)
+        self.bh = torch.zeros((T * B, 1, hd + 4), dtype=dt, device=dev)
+        self.bh[:, 0, :hd] = torch.stack([h(t, 0, "bias") for t in tr], 1).reshape(T * B, hd)
         self.bh[:, 0, hd] = 1.0
-        # heads, transposed for a multiply-and-reduce (a [2B, 1, 512] x [2B, 512, 3] bmm costs 17 us as a batched GEMV):
-        # [2B, A, 512 + 4] with the bias in column 512; the critic's single row is padded to the actor's width
-        wo = torch.zeros((B, 2, A, hd + 4), dtype=dt, device=dev)
+        # heads, transposed for a multiply-and-reduce (a [T B, 1, 512] x [T B, 512, 3] bmm costs 17 us as a batched GEMV):
+        # [T B, A, 512 + 4] with the bias in column 512; the critic's single row is padded to the actor's width
+        wo = torch.zeros((B, T, A, hd + 4), dtype=dt, device=dev)
         wo[:, 0, :, :hd] = h("actor", 2, "weight")
         wo[:, 0, :, hd] = h("actor", 2, "bias")
-        wo[:, 1, :1, :hd] = h("critic", 2, "weight")
-        wo[:, 1, :1, hd] = h("critic", 2, "bias")
-        self.wo = wo.reshape(2 * B, A, hd + 4)
+        if T == 2:
+            wo[:, 1, :1, :hd] = h("critic", 2, "weight")
+            wo[:, 1, :1, hd] = h("critic", 2, "bias")
+        self.wo = wo.reshape(T * B, A, hd + 4)
         if self._patch is None:
             def ones_col(G, L, K):
                 buf = torch.zeros((G, L, K + 4), dtype=dt, device=dev)
                 buf[:, :, K] = 1.0
                 return buf
-            self._patch = (ones_col(B, 169, 192), ones_col(2 * B, 25, 512), ones_col(2 * B, 9, 576))
+            self._patch = (ones_col(B, 169, 192), ones_col(T * B, 25, 512), ones_col(T * B, 9, 576))
 
     def _conv(self, x, w, b, stride):
         if self.use_fused_conv and RolloutPolicy._fused_conv_ok is not False:
@@ -308,24 +319,27 @@ class RolloutPolicy:
             else:
                 trunk(0, "actor")
                 trunk(1, "critic")
-            torch.baddbmm(self.bo, self._hid, self.wo, out=out)            # [2, N, A]
+            if n <= 256:   # a [N, 520] x [520, 3] matmul costs 11 us as a GEMM at these sizes; multiply-and-reduce: 4 us
+                torch.sum(self._hid.unsqueeze(2) * self.wo_t, dim=-1, out=out)
+            else:
+                torch.bmm(self._hid, self.wo, out=out)                      # [2, N, A]
             return out[0], out[1, :, 0]
-        B = self.B
+        B, T = self.B, len(self.trunks)
         p1, p2, p3 = self._patch
         # conv1: 2x2 taps over the 14x14x48 blocked frame -> 13x13 positions x 192
         p1[:, :, :192].copy_(x.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B, 169, 192))
-        h1 = torch.relu_(torch.bmm(p1, self.w1))                           # [B, 169, 64] = [B, 13, 13, (trunk, 32)]
+        h1 = torch.relu_(torch.bmm(p1, self.w1))                           # [B, 169, 32 T] = [B, 13, 13, (trunk, 32)]
         # conv2: 4x4 stride 2 over 13x13x32 per trunk -> 5x5 positions x 512
-        v = h1.view(B, 13, 13, 2, 32).unfold(1, 4, 2).unfold(2, 4, 2)      # [B, 5, 5, 2, 32, 4, 4]
-        p2[:, :, :512].copy_(v.permute(0, 3, 1, 2, 4, 5, 6).reshape(2 * B, 25, 512))
-        h2 = torch.relu_(torch.bmm(p2, self.w2))                           # [2B, 25, 64] = [2B, 5, 5, 64]
+        v = h1.view(B, 13, 13, T, 32).unfold(1, 4, 2).unfold(2, 4, 2)      # [B, 5, 5, T, 32, 4, 4]
+        p2[:, :, :512].copy_(v.permute(0, 3, 1, 2, 4, 5, 6).reshape(T * B, 25, 512))
+        h2 = torch.relu_(torch.bmm(p2, self.w2))                           # [T B, 25, 64] = [T B, 5, 5, 64]
         # conv3: 3x3 over 5x5x64 -> 3x3 positions x 576
-        v = h2.view(2 * B, 5, 5, 64).unfold(1, 3, 1).unfold(2, 3, 1)       # [2B, 3, 3, 64, 3, 3]
-        p3[:, :, :576].copy_(v.reshape(2 * B, 9, 576))
-        h3 = torch.relu_(torch.bmm(p3, self.w3))                           # [2B, 9, 64]
-        hid = torch.relu_(torch.baddbmm(self.bh, h3.view(2 * B, 1, 576), self.wh))    # [2B, 1, 512 + 4]
+        v = h2.view(T * B, 5, 5, 64).unfold(1, 3, 1).unfold(2, 3, 1)       # [T B, 3, 3, 64, 3, 3]
+        p3[:, :, :576].copy_(v.reshape(T * B, 9, 576))
+        h3 = torch.relu_(torch.bmm(p3, self.w3))                           # [T B, 9, 64]
+        hid = torch.relu_(torch.baddbmm(self.bh, h3.view(T * B, 1, 576), self.wh))    # [T B, 1, 512 + 4]
         if out is None:
-            out = torch.empty((2 * B, 1, A), dtype=x.dtype, device=x.device)
-        torch.sum(hid * self.wo, dim=-1, out=out.view(2 * B, A))           # heads (+ bias through the constant-one unit)
-        out = out.view(B, 2, A)
-        return out[:, 0], out[:, 1, 0]
+            out = torch.empty((T * B, 1, A), dtype=x.dtype, device=x.device)
+        torch.sum(hid * self.wo, dim=-1, out=out.view(T * B, A))           # heads (+ bias through the constant-one unit)
+        out = out.view(B, T, A)
+        return out[:, 0], (out[:, 1, 0] if T == 2 else None)

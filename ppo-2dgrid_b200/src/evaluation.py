@@ -63,10 +63,9 @@ def evaluate_seeds(policy, difficulty, size, seeds, device="cuda", max_steps=Non
     else:
         A = env.n_actions
         if lean:
-            rp = RolloutPolicy(policy, params=params)
-            heads = torch.zeros((2 * B, 1, A) if params is not None else (2, B, A), dtype=torch.float32, device=dev)
-            hv = heads.view(B, 2, A) if params is not None else None
-            logits, value = (hv[:, 0], hv[:, 1, 0]) if params is not None else (heads[0], heads[1, :, 0])
+            rp = RolloutPolicy(policy, params=params, actor_only=True)   # evaluation never reads the value
+            heads = torch.zeros((B, 1, A) if params is not None else (2, B, A), dtype=torch.float32, device=dev)
+            logits = heads.view(B, A) if params is not None else heads[0]
             policy_in = torch.empty((B, 14, 14, 48), dtype=torch.float32, device=dev)
         else:
             logits = torch.zeros((B, A), dtype=torch.float32, device=dev)

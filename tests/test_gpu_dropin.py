@@ -381,9 +381,11 @@ def _to_np(x):
     return x.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("N,n_actions", [(1, 3), (37, 3), (5000, 3), (70000, 3), (300, 7)])
-def test_symbolic_only_observations(N, n_actions):
-    """want_rgb=False: the state-phase-only kernel (no frames, no atlas): symbolic images, rewards, flags, poses."""
+@pytest.mark.parametrize("sym_kernel", [False, True], ids=["auto_kernel", "lane_per_env_kernel"])
+@pytest.mark.parametrize("N,n_actions", [(1, 3), (37, 3), (2048, 3), (5000, 3), (70000, 3), (300, 7)])
+def test_symbolic_only_observations(N, n_actions, sym_kernel):
+    """want_rgb=False: no frames are written -- the state-phase-only kernel (lane per env), or for batches of up to 2048
+    envs the warp-per-env kernel (automatic choice); both checked: symbolic images, rewards, flags, poses."""
     from merlin_b200 import BatchedMerlinEnv, codes, layouts
     from test_gpu_parity import _object_layouts
     rng = np.random.default_rng(N)
@@ -393,7 +395,10 @@ def test_symbolic_only_observations(N, n_actions):
     else:
         enc, agent = _object_layouts(rng, 64, 11)
     env = BatchedMerlinEnv(N, enc=enc, agent=agent, device="cuda:0", n_actions=n_actions, max_steps=13, want_rgb=False)
-    assert env.obs is None and "sym" in env.step_kernel()
+    assert env.obs is None and ("warp" if N <= 2048 else "sym") in env.step_kernel()
+    if sym_kernel:
+        env.set_kernel_choice(5)
+        assert "sym" in env.step_kernel()
     ref = fast.OracleVecEnv(N, enc, agent, n_actions=n_actions, max_steps=13, want_rgb=False)
     rgb, sym = env.reset()
     assert rgb is None and np.array_equal(_to_np(sym), ref.reset()[1])
