@@ -215,7 +215,7 @@ class RolloutPolicy:
                 w[:, :hd] = h(t, 0, "weight").view(-1, 64, 3, 3).permute(2, 3, 1, 0).reshape(576, hd)
                 bias = torch.zeros(hd + 8, dtype=dt, device=dev)
                 bias[:hd] = h(t, 0, "bias")
-                bias[hd] = 1.0
+                bias[hd:hd + 1].fill_(1.0)   # (an integer-indexed `bias[hd] = 1.0` is a host-to-device copy: illegal under capture)
                 self.wh[t], self.bh[t] = w, bias
             # both heads over the trunks at once, bias in row 512; the critic's single column is padded to the actor's width
             self.wo = torch.zeros((2, hd + 8, A), dtype=dt, device=dev)          # for a batched matmul
@@ -258,7 +258,7 @@ class RolloutPolicy:
         self.wh[:, :, :hd] = wh.reshape(T * B, hd, 64, 9).permute(0, 3, 2, 1).reshape(T * B, 576, hd)
         self.bh = torch.zeros((T * B, 1, hd + 4), dtype=dt, device=dev)
         self.bh[:, 0, :hd] = torch.stack([h(t, 0, "bias") for t in tr], 1).reshape(T * B, hd)
-        self.bh[:, 0, hd] = 1.0
+        self.bh[:, 0, hd].fill_(1.0)
         # heads, transposed for a multiply-and-reduce (a [T B, 1, 512] x [T B, 512, 3] bmm costs 17 us as a batched GEMV):
         # [T B, A, 512 + 4] with the bias in column 512; the critic's single row is padded to the actor's width
         wo = torch.zeros((B, T, A, hd + 4), dtype=dt, device=dev)
@@ -271,7 +271,7 @@ class RolloutPolicy:
         if self._patch is None:
             def ones_col(G, L, K):
                 buf = torch.zeros((G, L, K + 4), dtype=dt, device=dev)
-                buf[:, :, K] = 1.0
+                buf[:, :, K].fill_(1.0)
                 return buf
             self._patch = (ones_col(B, 169, 192), ones_col(T * B, 25, 512), ones_col(T * B, 9, 576))
 

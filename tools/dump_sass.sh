@@ -21,7 +21,7 @@ cuobjdump -sass "$so" 2>/dev/null | python3 -c '
 import re, sys, subprocess, collections
 cur, stats = None, collections.OrderedDict()
 pat = re.compile(r"^\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)")
-keep = ("STG", "LDG", "LDS", "STS", "UBLKCP", "UTMA", "ATOM", "RED", "VOTE", "SHFL", "BAR", "BREV", "PRMT", "LDC", "STL", "LDL", "FENCE", "MEMBAR")
+keep = ("STG", "LDG", "LDS", "STS", "UBLKCP", "UTMA", "ATOM", "RED", "VOTE", "SHFL", "BAR", "BREV", "STL", "LDL", "FENCE", "MEMBAR", "CCTL", "SYNCS")
 for line in sys.stdin:
     m = re.search(r"Function : (\S+)", line)
     if m:
