@@ -730,11 +730,15 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, c
 #define MERLIN_WARP_THREADS 256
 #define MERLIN_WARP_CTAS 4
 #endif
+// RGB batches of at least this many envs launch the warp kernel with programmatic dependent launch (see the kernel)
+#ifndef MERLIN_WARP_PDL_MIN_ENVS
+#define MERLIN_WARP_PDL_MIN_ENVS 4096
+#endif
 constexpr int kWarpKernelThreads = MERLIN_WARP_THREADS;
 constexpr int kWarpKindBytes = 128;          // 49 premultiplied kinds (u16) per warp, padded
 constexpr int kPairChunks = 2 * kUnitsPerRow / 2;   // 21 16-byte chunks per pair of pixel rows
 
-template <int STEP>
+template <int STEP, bool PDL>
 __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kernel_warp(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -745,10 +749,22 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
   uint16_t* kq = reinterpret_cast<uint16_t*>(smem + kAtlasBytes + warp * kWarpKindBytes);   // this warp's 49 kinds * 192
 
   int e = blockIdx.x * warps_per_cta + warp;
-  // first env's state / action: in flight while the atlas is staged
   int4 st_next = make_int4(0, 0, 0, 0);
   long long act_next = 0;
-  if (e < p.N) {
+  if (PDL) {
+    // Programmatic dependent launch (RGB batches of >= 4096 envs): the kernel is launched with
+    // cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled while the PREVIOUS kernel of the
+    // stream is still draining its stores.  Everything up to griddepcontrol.wait touches only data no kernel writes (the
+    // atlas and the tile mask are written by synchronous uploads): launch latency and the two-round-trip atlas staging
+    // overlap the predecessor's tail.  After the wait the predecessor has completed and its writes (state, the policy's
+    // logits, ...) are visible.  launch_dependents at once: a following env step may start its own prologue under THIS
+    // kernel's store phase (all CTAs of a <= 24 576-env batch are resident together: early arrivals cannot starve it).
+    // Measured (B200, CUDA-graph replay / eager back to back, us per step): 4096 envs 10.4 -> 9.7 / 12.3 -> 10.0,
+    // 16 384 envs 28.1 -> 27.2 / 29.9 -> 27.5, 24 576 envs 40.9 -> 40.0; at 1024 envs graph replay gets SLOWER (4.9 ->
+    // 8.0: the programmatic edge costs more than it hides), hence the size threshold.
+    asm volatile("griddepcontrol.launch_dependents;");
+  } else if (e < p.N) {
+    // first env's state / action: in flight while the atlas is staged
     st_next = p.state[e];
     if (STEP == 1) act_next = p.actions[e];
   }
@@ -762,6 +778,13 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
 #pragma unroll
         for (int i = 0; i < 6; ++i) dst[i] = __ldg(src + i);
       }
+    }
+  }
+  if (PDL) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (e < p.N) {
+      st_next = p.state[e];
+      if (STEP == 1) act_next = p.actions[e];
     }
   }
   __syncthreads();
@@ -1284,11 +1307,24 @@ static cudaError_t launch_warp_kernel(const EnvParams& p, const LaunchCtx& ctx, 
   const size_t smem = kAtlasBytes + warps * kWarpKindBytes;
   int& blocks_per_sm = ctx.occ[kSlotWarp + STEP];
   if (!blocks_per_sm) {
-    cudaError_t err = resident_ctas(env_kernel_warp<STEP>, kWarpKernelThreads, smem, blocks_per_sm);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = resident_ctas(env_kernel_warp<STEP, false>, kWarpKernelThreads, smem, blocks_per_sm);
+    if (err == cudaSuccess) {
+      int same = 0;
+      err = resident_ctas(env_kernel_warp<STEP, true>, kWarpKernelThreads, smem, same);
+    }
+    if (err != cudaSuccess) { blocks_per_sm = 0; return err; }
   }
   const int grid = min(ctx.sm_count * blocks_per_sm, (p.N + warps - 1) / warps);
-  env_kernel_warp<STEP><<<grid, kWarpKernelThreads, smem, stream>>>(p);
+  if (p.obs_rgb != nullptr && p.N >= MERLIN_WARP_PDL_MIN_ENVS) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kWarpKernelThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, env_kernel_warp<STEP, true>, p);
+  }
+  env_kernel_warp<STEP, false><<<grid, kWarpKernelThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -326,17 +326,26 @@ class RolloutPolicy:
             return out[0], out[1, :, 0]
         B, T = self.B, len(self.trunks)
         p1, p2, p3 = self._patch
-        # conv1: 2x2 taps over the 14x14x48 blocked frame -> 13x13 positions x 192
-        p1[:, :, :192].copy_(x.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B, 169, 192))
-        h1 = torch.relu_(torch.bmm(p1, self.w1))                           # [B, 169, 32 T] = [B, 13, 13, (trunk, 32)]
-        # conv2: 4x4 stride 2 over 13x13x32 per trunk -> 5x5 positions x 512
-        v = h1.view(B, 13, 13, T, 32).unfold(1, 4, 2).unfold(2, 4, 2)      # [B, 5, 5, T, 32, 4, 4]
-        p2[:, :, :512].copy_(v.permute(0, 3, 1, 2, 4, 5, 6).reshape(T * B, 25, 512))
-        h2 = torch.relu_(torch.bmm(p2, self.w2))                           # [T B, 25, 64] = [T B, 5, 5, 64]
-        # conv3: 3x3 over 5x5x64 -> 3x3 positions x 576
-        v = h2.view(T * B, 5, 5, 64).unfold(1, 3, 1).unfold(2, 3, 1)       # [T B, 3, 3, 64, 3, 3]
-        p3[:, :, :576].copy_(v.reshape(T * B, 9, 576))
-        h3 = torch.relu_(torch.bmm(p3, self.w3))                           # [T B, 9, 64]
+        # the three convolutions run in the precision PyTorch runs convolutions in (TF32 tensor cores unless
+        # torch.backends.cudnn.allow_tf32 was switched off) -- what cuDNN does for the same layers in the loss and in the
+        # shared-weight path; the linear layers below stay in fp32 like nn.Linear
+        mm = torch.backends.cuda.matmul
+        keep, mm.allow_tf32 = mm.allow_tf32, bool(torch.backends.cudnn.allow_tf32) or mm.allow_tf32
+        try:
+            # conv1: 2x2 taps over the 14x14x48 blocked frame -> 13x13 positions x 192
+            # (the patch buffers are viewed in the unfolded shape, so each im2col is ONE strided copy, no intermediate)
+            p1[:, :, :192].unflatten(2, (48, 2, 2)).unflatten(1, (13, 13)).copy_(x.unfold(1, 2, 1).unfold(2, 2, 1))
+            h1 = torch.relu_(torch.bmm(p1, self.w1))                       # [B, 169, 32 T] = [B, 13, 13, (trunk, 32)]
+            # conv2: 4x4 stride 2 over 13x13x32 per trunk -> 5x5 positions x 512
+            v = h1.view(B, 13, 13, T, 32).unfold(1, 4, 2).unfold(2, 4, 2)  # [B, 5, 5, T, 32, 4, 4]
+            p2[:, :, :512].unflatten(2, (32, 4, 4)).unflatten(1, (5, 5)).unflatten(0, (B, T)).copy_(v.permute(0, 3, 1, 2, 4, 5, 6))
+            h2 = torch.relu_(torch.bmm(p2, self.w2))                       # [T B, 25, 64] = [T B, 5, 5, 64]
+            # conv3: 3x3 over 5x5x64 -> 3x3 positions x 576
+            v = h2.view(T * B, 5, 5, 64).unfold(1, 3, 1).unfold(2, 3, 1)   # [T B, 3, 3, 64, 3, 3]
+            p3[:, :, :576].unflatten(2, (64, 3, 3)).unflatten(1, (3, 3)).copy_(v)
+            h3 = torch.relu_(torch.bmm(p3, self.w3))                       # [T B, 9, 64]
+        finally:
+            mm.allow_tf32 = keep
         hid = torch.relu_(torch.baddbmm(self.bh, h3.view(T * B, 1, 576), self.wh))    # [T B, 1, 512 + 4]
         if out is None:
             out = torch.empty((T * B, 1, A), dtype=x.dtype, device=x.device)

@@ -65,6 +65,7 @@ class FOMAML:
         self._prefetch = None  # (seeds, thread, result box) of prefetch_tasks
         self._envs = {}  # task-batch size -> cached BatchedMerlinEnv
         self._graphs = {}  # (env, steps, per-task weights?) -> captured rollout
+        self._phase_graphs = {}  # (phase, env, k) -> captured loss / gradient pass
         self.use_cuda_graph = self.device.type == "cuda"
 
     # ---- helpers ------------------------------------------------------------------------------------------
@@ -122,7 +123,7 @@ class FOMAML:
 
     # ---- rollouts -----------------------------------------------------------------------------------------
     @torch.no_grad()
-    def collect_trajectory(self, env, policy, steps=20, task_seed=None, params=None):
+    def collect_trajectory(self, env, policy, steps=20, task_seed=None, params=None, params_static=False):
         """`steps` transitions from a fresh reset.  `env`: a BatchedMerlinEnv whose B envs are B tasks (`policy`
         acts for all of them; `params` = stacked per-task weights evaluates task b with its own weights), or a
         reference-style single env (then `task_seed` re-seeds every reset, as in the reference).
@@ -131,7 +132,7 @@ class FOMAML:
         if not isinstance(env, BatchedMerlinEnv):
             return self._collect_single(env, policy, steps, task_seed)
         if self.use_cuda_graph and policy is self.meta_policy:
-            return self._collect_graphed(env, steps, params)
+            return self._collect_graphed(env, steps, params, params_static)
         buf = self._rollout_buffers(env, steps)
         self._rollout_body(env, policy, params, steps, buf)
         return self._rollout_result(env, buf, steps)
@@ -215,18 +216,25 @@ class FOMAML:
             out["obs"] = buf["obs"][:steps]
         return out
 
-    def _collect_graphed(self, env, steps, params):
+    def _collect_graphed(self, env, steps, params, params_static=False):
         """The whole k-step rollout (input rendering, fused policy network, fused sample/step/store transition)
         replayed from one CUDA graph per (env, steps, shared | per-task weights).  Per-task weights are copied into the
         graph's static stacked tensors before each replay (the graph re-packs them); the meta-policy's own parameters
         are updated in place by the optimiser, so a graph over them stays valid.  The returned tensors are the graph's
         buffers: valid until the next rollout of that kind."""
-        key = (id(env), steps, params is not None)
+        # params_static: `params` are themselves static tensors (outputs of a captured adapt pass): the rollout graph
+        # reads them in place, nothing is copied per replay
+        ident = id(next(iter(params.values()))) if (params is not None and params_static) else 0
+        key = (id(env), steps, params is not None, ident)
         g = self._graphs.get(key)
         if g is None:
             buf = self._rollout_buffers(env, steps)
-            static = None if params is None else {n: torch.empty_like(p) for n, p in params.items()}
-            if static is not None:
+            if params is None:
+                static = None
+            elif params_static:
+                static = {n: p.detach() for n, p in params.items()}
+            else:
+                static = {n: torch.empty_like(p) for n, p in params.items()}
                 for n in static:
                     static[n].copy_(params[n])
             side = torch.cuda.Stream(env.device)
@@ -242,11 +250,30 @@ class FOMAML:
                 self._rollout_body(env, self.meta_policy, static, steps, buf)
             g = self._graphs[key] = (graph, buf, static)
         graph, buf, static = g
-        if static is not None:
+        if static is not None and not params_static:
             for n in static:
                 static[n].copy_(params[n])
         graph.replay()
         return self._rollout_result(env, buf, steps)
+
+    def _phase(self, key, fn):
+        """Run `fn` from a CUDA graph captured on first use (after three eager warm-up runs on a side stream: cuDNN plans,
+        autograd, allocator); returns fn's outputs -- the graph's static tensors, rewritten by every replay."""
+        g = self._phase_graphs.get(key)
+        if g is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn()
+            g = self._phase_graphs[key] = (graph, out)
+        g[0].replay()
+        return g[1]
 
     def _act(self, policy, params, obs, **kw):
         """Sampled action, its log-probability and the value for one frame per task (torch-side sampling: the
@@ -296,6 +323,15 @@ class FOMAML:
         """PPO-clip loss of the reference (src/fomaml.py:110-156).  Single trajectory -> (loss, stats) as in the
         reference.  Task-batched trajectory (`[k, B]`) -> (per-task loss `[B]`, stats averaged over tasks); with
         `params` (stacked per-task weights) task b is evaluated under its own weights."""
+        total, stat5 = self._loss_terms(batch, policy, params, want_stats)
+        if not want_stats:  # internal callers that discard the statistics skip their read-back (a host sync)
+            return total, {"loss": total}
+        s = stat5.tolist()
+        return total, {"loss": total, "pi_loss": s[0], "v_loss": s[1], "entropy": s[2], "kl": s[3], "clipfrac": s[4]}
+
+    def _loss_terms(self, batch, policy, params=None, want_stats=True):
+        """The loss without any host synchronisation (capturable in a CUDA graph): (loss, f32[5] = pi_loss, v_loss,
+        entropy, kl, clipfrac as a device tensor, or None)."""
         adv, ret = self._advantages(batch)
         old_logp = batch["logp"].detach()
         act = batch["act"]
@@ -329,14 +365,13 @@ class FOMAML:
         v_loss = ((new_vals - ret) ** 2).mean(0)
         ent = entropy.mean(0)
         total = pi_loss + self.vf_coef * v_loss - self.ent_coef * ent
-        if not want_stats:  # internal callers that discard the statistics skip their read-back (a host sync)
-            return total, {"loss": total}
+        if not want_stats:
+            return total, None
         with torch.no_grad():
             kl = (old_logp - new_logp).mean()
             clipfrac = (torch.abs(ratio - 1.0) > self.clip_eps).float().mean()
-            s = torch.stack([pi_loss.mean(), v_loss.mean(), ent.mean(), kl, clipfrac]).tolist()
-        stats = {"loss": total, "pi_loss": s[0], "v_loss": s[1], "entropy": s[2], "kl": s[3], "clipfrac": s[4]}
-        return total, stats
+            stat5 = torch.stack([pi_loss.mean(), v_loss.mean(), ent.mean(), kl, clipfrac])
+        return total, stat5
 
     def _fmt_tasks(self, obs):
         o = obs.transpose(0, 1)  # [B, k, 56, 56, 3]
@@ -390,22 +425,36 @@ class FOMAML:
         if my_seeds:
             B = len(my_seeds)
             env = self._task_env(my_seeds)
+            graphed = self.use_cuda_graph and self._lean(env, meta)
             # inner loop: support rollout under the shared meta weights, one SGD step per task
             support = self.collect_trajectory(env, meta, steps=k_support)
-            fast = _stack(meta, B)
-            s_loss, _ = self.compute_loss(support, meta, params=fast, want_stats=False)
-            fast = self._inner_step(fast, s_loss, names, self.lr_inner)
+
+            def adapt():
+                fast0 = _stack(meta, B)
+                s_loss, _ = self._loss_terms(support, meta, fast0, want_stats=False)
+                return self._inner_step(fast0, s_loss, names, self.lr_inner)
+            # (the loss / gradient passes are launch-bound too -- a few hundred small kernels plus vmap's host-side
+            # dispatch -- so each is captured once per (env, k) and replayed: the rollouts' buffers they read and the
+            # per-task weights they write are the graphs' own static tensors)
+            fast = self._phase(("adapt", id(env), k_support), adapt) if graphed else adapt()
             # outer loop: query rollout under each task's adapted weights, first-order gradient
-            query = self.collect_trajectory(env, meta, steps=k_query, params=fast)
-            lens, rews = query["ep_lens"], query["ep_rews"]
-            q_loss, query_stats = self.compute_loss(query, meta, params=fast)
-            gq = torch.autograd.grad(q_loss.sum(), [fast[n] for n in names])
-            grads_sum = [gi.sum(0) for gi in gq]
-            loss_sum = q_loss.detach().double().sum()
-            query_stats = {**query_stats, "loss": q_loss.detach().mean()}
-            with torch.no_grad():  # keep `fast_policy` = the last task's adapted weights, as the reference leaves it
-                for n, p in self.fast_policy.named_parameters():
-                    p.copy_(fast[n][-1])
+            query = self.collect_trajectory(env, meta, steps=k_query, params=fast, params_static=graphed)
+
+            def meta_grad():
+                leaves = {n: fast[n].detach().requires_grad_(True) for n in names}
+                q_loss, stat5 = self._loss_terms(query, meta, leaves)
+                gq = torch.autograd.grad(q_loss.sum(), [leaves[n] for n in names])
+                with torch.no_grad():  # keep `fast_policy` = the last task's adapted weights, as the reference leaves it
+                    for n, p in self.fast_policy.named_parameters():
+                        p.copy_(fast[n][-1])
+                    sums = [gi.sum(0) for gi in gq]
+                    return sums, q_loss.detach().double().sum(), torch.cat([stat5, q_loss.detach().mean().reshape(1)])
+            grads_sum, loss_sum, stat6 = (self._phase(("meta_grad", id(env), k_query), meta_grad) if graphed
+                                          else meta_grad())
+            lens, rews = query["ep_lens"], query["ep_rews"]   # first host read-back of the iteration: everything is queued
+            s6 = stat6.tolist()
+            query_stats = {"pi_loss": s6[0], "v_loss": s6[1], "entropy": s6[2], "kl": s6[3], "clipfrac": s6[4],
+                           "loss": s6[5]}
 
         # the one collective: SUM of the accumulated meta-gradient (and of the logged loss), then / global #tasks
         flat = torch.cat([gi.reshape(-1) for gi in grads_sum] + [loss_sum.reshape(1).to(grads_sum[0].dtype)])

@@ -298,3 +298,42 @@ def test_steps_and_renders_alternating_between_streams_stay_ordered():
     env.rearm()
     obs, *_ = env.step(acts[0])
     assert np.array_equal(_np(obs), ref.step(_np(acts[0]))[0])
+
+
+# ---- state save / restore (merlin_env_read_state / merlin_env_write_state) ----------------------------------------
+def test_write_state_resumes_a_rollout_bit_exactly_and_validates():
+    """Save the env state mid-rollout, run on, restore it into a SECOND handle and replay the same actions: identical
+    observations, rewards and flags (the state words are the whole state for immutable grids); staggered episode clocks
+    make envs truncate at the steady-state rate; bad states are rejected."""
+    BatchedMerlinEnv, _, _ = _mods()
+    cells, agent, enc = _pool(96)
+    N = 4096
+    envs = [BatchedMerlinEnv(N, cells, agent, width=16, height=16, max_steps=64, device=DEV) for _ in range(2)]
+    rng = np.random.default_rng(3)
+    acts = [torch.as_tensor(rng.integers(0, 3, N), device=DEV) for _ in range(24)]
+    a, b = envs
+    a.reset(); b.reset()
+    for t in range(8):
+        a.step(acts[t])
+    st, epr = a.state_raw()
+    tail = [tuple(x.clone() for x in a.step(acts[t])[:4]) for t in range(8, 24)]
+    b.load_state_raw(st, epr)
+    for t in range(8, 24):
+        obs, r, te, tr, info = b.step(acts[t])
+        want = tail[t - 8]
+        assert torch.equal(obs, want[0]) and torch.equal(r, want[1]) and torch.equal(te, want[2]) and torch.equal(tr, want[3]), t
+    assert np.array_equal(a.pose_numpy(), b.pose_numpy())
+    # staggered clocks: truncations arrive at ~N / max_steps per step instead of all at step 64
+    b.reset()
+    b.stagger_episode_clocks(seed=1)
+    assert len(np.unique(b.state_numpy()["step_count"])) == 64
+    n_trunc = [int(b.step(acts[t])[3].sum()) for t in range(16)]
+    assert min(n_trunc) > 0 and max(n_trunc) < 4 * N // 64
+    bad = st.copy(); bad[0, 2] = 10_000          # layout index outside the pool
+    with pytest.raises(ValueError):
+        b.load_state_raw(bad)
+    bad = st.copy(); bad[5, 1] = 64               # step_count == max_steps
+    with pytest.raises(ValueError):
+        b.load_state_raw(bad)
+    with pytest.raises(ValueError):
+        b.load_state_raw(st[:10])
