@@ -225,7 +225,9 @@ int merlin_env_set_kernel_choice(merlin_env_t* h, int choice);
 int merlin_env_set_observation_path(merlin_env_t* h, int path);
 /* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
  * 3 = CTA-tile kernel, 4 = CTA-tile kernel with the frames stored by the TMA unit (cp.async.bulk), 5 = symbolic-only
- * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out.
+ * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out,
+ * 7 = four envs per warp (steps of the three-action / no-shaping-wrapper configuration with RGB frames -- what
+ * "automatic" picks for those at small batch sizes; anything else asked of it runs kernel 2).
  * All kernels produce identical results for the outputs they write; "automatic" never picks 4 or 6 (measured slower). */
 int merlin_set_kernel_choice(int choice);
 /* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: how gen_obs is computed.  0 = automatic (default): the symbolic-only kernel works
@@ -237,7 +239,8 @@ int merlin_set_observation_path(int path);
 const char* merlin_env_step_kernel(merlin_env_t* h, int rgb);
 
 /* GAE + returns over a time-major [T][N] rollout (all DEVICE f32). done = terminated|truncated as 0/1.
- * adv[t] = delta_t + gamma*lam*(1-done_t)*adv[t+1]; ret = val + adv.  fp32, unfused, reference op order. */
+ * adv[t] = delta_t + gamma*lam*(1-done_t)*adv[t+1]; ret = val + adv.  fp32, unfused, reference op order.
+ * The outputs must not alias the inputs (rows are re-read after later rows have been written). */
 int merlin_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv, float* ret,
                int32_t T, int32_t N, double gamma, double lam, void* stream);
 

@@ -627,12 +627,14 @@ int merlin_env_bad_actions(merlin_env_t* h, uint64_t* count) {
 int64_t merlin_env_launch_count(merlin_env_t* h) { return h ? h->launches : 0; }
 
 const char* merlin_env_step_kernel(merlin_env_t* h, int rgb) {
-  return h ? step_kernel_name(h->cfg.n_envs, rgb != 0, launch_ctx(h)) : "";
+  if (!h) return "";
+  constexpr uint32_t kNotLean = MERLIN_F_SEVEN_ACTIONS | MERLIN_F_STUCK_PENALTY | MERLIN_F_EXPLORE_BONUS;
+  return step_kernel_name(h->cfg.n_envs, (rgb & 1) != 0, (h->cfg.flags & kNotLean) == 0, launch_ctx(h));
 }
 
 static int check_kernel_choice(int choice, int lowest) {
-  if (choice < lowest || choice > 6)
-    return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile), 4 (tile, TMA frame stores), 5 (symbolic-only) or 6 (ordered groups)");
+  if (choice < lowest || choice > 7)
+    return fail(MERLIN_EINVAL, "kernel choice must be 0 (auto), 1 (group), 2 (warp), 3 (tile), 4 (tile, TMA frame stores), 5 (symbolic-only), 6 (ordered groups) or 7 (four envs per warp)");
   return MERLIN_OK;
 }
 static int check_observation_path(int path, int lowest) {

@@ -13,6 +13,10 @@ constexpr int kThreads = 256;                 // 8 warps per CTA
 #ifndef MERLIN_AUTO_RGB_CHOICE
 #define MERLIN_AUTO_RGB_CHOICE(N, SMS) ((N) <= 24576 ? 2 : 3)
 #endif
+// automatic choice 2 becomes 7 (env_kernel_quad) where that kernel applies: three actions, no shaping wrapper, RGB frames
+#ifndef MERLIN_AUTO_QUAD
+#define MERLIN_AUTO_QUAD(N) ((N) >= 6144 && (N) <= 12288)
+#endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576
 constexpr int kKindStride = 52;               // 49 tile kinds per env, padded: odd word stride -> conflict-free lanes
@@ -74,7 +78,7 @@ struct EnvParams {
 
 // Per-handle launch context: kernel choice, observation path and the occupancy cache live in the handle (a process may
 // hold several handles on several devices, driven from different threads).
-constexpr int kOccSlots = 40;
+constexpr int kOccSlots = 44;
 struct LaunchCtx {
   int sm_count;
   int kernel_choice;      // 0 = automatic, 1..6 as merlin_set_kernel_choice
@@ -84,10 +88,12 @@ struct LaunchCtx {
 
 // kernel choice: 0 = automatic, 1 = env_kernel (warp owns a group), 2 = env_kernel_warp (warp per env), 3 = env_kernel_tile,
 // 4 = env_kernel_tile_tma (tile kernel, frames through cp.async.bulk), 5 = env_kernel_sym (state phase only: any RGB
-// output pointer is ignored), 6 = env_kernel_ordered (group kernel, groups handed out in order)
+// output pointer is ignored), 6 = env_kernel_ordered (group kernel, groups handed out in order), 7 = env_kernel_quad (four
+// envs per warp; steps of the lean configuration with RGB frames -- anything else asked of it runs choice 2)
 // observation path: 0 = automatic (row-parallel obs_swar.cuh in the symbolic-only kernel when W >= 7), 1 = per-cell
 // everywhere, 2 = row-parallel in every kernel that has it (symbolic-only, tile, ordered)
-const char* step_kernel_name(int n_envs, bool rgb, const LaunchCtx& ctx);
+// quad_ok: three actions, no shaping wrapper (what env_kernel_quad serves)
+const char* step_kernel_name(int n_envs, bool rgb, bool quad_ok, const LaunchCtx& ctx);
 cudaError_t launch_env_step(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream);
 cudaError_t launch_env_reset(const EnvParams& p, const LaunchCtx& ctx, cudaStream_t stream);
 // Frames from stored symbolic observations (RGBImgPartialObsWrapper.observation as a batch op, with an optional

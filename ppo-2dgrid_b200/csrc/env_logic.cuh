@@ -313,6 +313,19 @@ MERLIN_HD uint64_t visibility(uint64_t transp) {
   return vis;
 }
 
+// The same with one row per BYTE (row vj in bits 8*vj .. 8*vj+6), in and out: what env_kernel_quad's lanes exchange.
+MERLIN_HD uint64_t visibility_rows(uint64_t transp_rows) {
+  uint64_t vis = 0;
+  uint32_t seed = 1u << (kView / 2);
+#pragma unroll
+  for (int vj = kView - 1; vj >= 0; --vj) {
+    uint32_t v;
+    seed = vis_row(seed, (uint32_t)(transp_rows >> (8 * vj)) & 0x7f, v);
+    vis |= (uint64_t)v << (8 * vj);
+  }
+  return vis;
+}
+
 // Atlas slot shown for the agent cell (view (3,6)): the carried object under the agent triangle.
 MERLIN_HD uint32_t agent_kind(uint32_t carry) {
   return carry == 0 ? KIND_AGENT : ((carry & 0x70) | ((carry & 0xf) + 8));  // key/ball/box -> 13/14/15

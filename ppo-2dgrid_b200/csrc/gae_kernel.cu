@@ -71,9 +71,76 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
   }
 }
 
+// Small rollouts (a few thousand envs: one warp or less per SM in the kernel above, whose run time is then T / kChunk
+// dependent memory round trips plus the chain): a CTA owns 32 envs and a window of TC time steps at once.
+//   phase 1  ALL warps load the window's rew / val / done rows (every load of the window in flight together) and
+//            compute what does not depend on the scan -- delta[t] and c[t] = (gamma * lam) * mask[t] -- into shared memory;
+//   phase 2  ONE warp (lane = env) runs the recurrence gae = delta[t] + c[t] * gae from shared memory: two dependent
+//            fp32 operations per step;
+//   phase 3  ALL warps write adv[t] and ret[t] = val[t] + adv[t], coalesced.
+// Same operations in the same order as gae_kernel (and the reference loop): bit-identical results.
+__global__ void __launch_bounds__(256) gae_tile_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                       const float* __restrict__ done, const float* __restrict__ last_val,
+                                                       float* __restrict__ adv, float* __restrict__ ret, const int T,
+                                                       const int N, const int TC, const double gamma, const float g32,
+                                                       const float gl32) {
+  extern __shared__ float sm[];
+  float* s_delta = sm;                 // [TC][32]
+  float* s_c = sm + TC * 32;           // [TC][32]
+  float* s_a = sm + 2 * TC * 32;       // [TC][32]   (3 x 128 x 32 floats = 48 KB: no opt-in needed)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool ok = n < N;
+  float gae = 0.f;
+  for (int t_hi = T - 1; t_hi >= 0; t_hi -= TC) {
+    const int len = min(TC, t_hi + 1), t_lo = t_hi - len + 1;
+    if (ok) {
+      for (int j = w; j < len; j += nw) {
+        const int t = t_lo + j;
+        const size_t k = (size_t)t * N + n;
+        const float r = rew[k], v = val[k], d = done[k];
+        // gamma * next_val: python double product rounded to f32 at t = T-1, else gamma(f32) * values[t+1]
+        const float gnext = t == T - 1 ? (float)(gamma * (double)last_val[n]) : __fmul_rn(g32, val[k + N]);
+        const float mask = __fsub_rn(1.0f, d);
+        s_delta[j * 32 + lane] = __fsub_rn(__fadd_rn(r, __fmul_rn(gnext, mask)), v);
+        s_c[j * 32 + lane] = __fmul_rn(gl32, mask);
+      }
+    }
+    __syncthreads();
+    if (w == 0 && ok) {
+#pragma unroll 8
+      for (int j = len - 1; j >= 0; --j) {
+        gae = __fadd_rn(s_delta[j * 32 + lane], __fmul_rn(s_c[j * 32 + lane], gae));
+        s_a[j * 32 + lane] = gae;
+      }
+    }
+    __syncthreads();
+    if (ok) {
+      for (int j = w; j < len; j += nw) {
+        const size_t k = (size_t)(t_lo + j) * N + n;
+        const float a = s_a[j * 32 + lane];
+        adv[k] = a;
+        ret[k] = __fadd_rn(val[k], a);   // second read of the row: L1 / L2
+      }
+    }
+    __syncthreads();   // the next window overwrites s_a
+  }
+}
+
+#ifndef MERLIN_GAE_TILE_MAX_ENVS
+#define MERLIN_GAE_TILE_MAX_ENVS 16384   // up to here the tile kernel runs (<= 512 CTAs); above, one thread per env
+#endif
+
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream) {
   // small rollouts: 32-thread blocks spread the envs over more SMs (4096 envs -> 128 blocks instead of 32)
+  if (N <= MERLIN_GAE_TILE_MAX_ENVS) {
+    const int TC = T < 128 ? (T < 1 ? 1 : T) : 128;
+    const size_t smem = (size_t)3 * TC * 32 * sizeof(float);
+    gae_tile_kernel<<<(N + 31) / 32, 256, smem, stream>>>(rew, val, done, last_val, adv, ret, T, N, TC, gamma, (float)gamma,
+                                                          (float)(gamma * lam));
+    return cudaGetLastError();
+  }
   const bool large = N >= 32768;
   const int threads = N >= 128 * 148 * 4 ? 128 : 32;
   const int blocks = (N + threads - 1) / threads;

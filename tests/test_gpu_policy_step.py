@@ -35,8 +35,8 @@ def _pool(n=64, diff="mediumhard", size=16, first=4200):
     return cells, agent, codes.unpack_to_encoding(cells, size, size)
 
 
-@pytest.mark.parametrize("choice,rgb", [(1, True), (2, True), (3, True), (6, True), (5, False)],
-                         ids=["group", "warp", "tile", "ordered", "symbolic_only"])
+@pytest.mark.parametrize("choice,rgb", [(1, True), (2, True), (3, True), (6, True), (7, True), (5, False)],
+                         ids=["group", "warp", "tile", "ordered", "quad", "symbolic_only"])
 @pytest.mark.parametrize("N", [33, 1000])
 def test_policy_step_env_half_bit_exact_and_sampler_matches_restatement(choice, rgb, N):
     BatchedMerlinEnv, _, _ = _mods()
@@ -87,7 +87,7 @@ def test_policy_step_same_draws_under_every_kernel_mapping_and_reseed():
     gen = torch.Generator(device=DEV).manual_seed(5)
     all_logits = torch.randn((T, N, 3), generator=gen, device=DEV) * 1.5
     runs = {}
-    for choice in (1, 2, 3, 4, 6, 5):
+    for choice in (1, 2, 3, 4, 6, 7, 5):
         env = BatchedMerlinEnv(N, cells, agent, width=16, height=16, max_steps=9, device=DEV)
         env.set_kernel_choice(choice)
         env.seed_sampler(31337)
@@ -110,7 +110,7 @@ def test_policy_step_same_draws_under_every_kernel_mapping_and_reseed():
             env.reset()
             env.policy_step(io)
             assert not torch.equal(io.action, runs[1][0][0])
-    for choice in (2, 3, 4, 6, 5):
+    for choice in (2, 3, 4, 6, 7, 5):
         for a, b in zip(runs[1], runs[choice]):
             assert torch.equal(a, b), choice
     a = runs[1][0]
