@@ -226,9 +226,9 @@ int merlin_env_set_observation_path(merlin_env_t* h, int path);
 /* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: 0 = automatic (default), 1 = warp-owns-a-group kernel, 2 = warp-per-env kernel,
  * 3 = CTA-tile kernel, 4 = CTA-tile kernel with the frames stored by the TMA unit (cp.async.bulk), 5 = symbolic-only
  * kernel (writes no RGB frames; what "automatic" picks when obs_rgb is NULL), 6 = group kernel with in-order hand-out,
- * 7 = four envs per warp (steps of the three-action / no-shaping-wrapper configuration with RGB frames -- what
- * "automatic" picks for those at small batch sizes; anything else asked of it runs kernel 2).
- * All kernels produce identical results for the outputs they write; "automatic" never picks 4 or 6 (measured slower). */
+ * 7 = four envs per warp (steps of the three-action / no-shaping-wrapper configuration with RGB frames; anything else
+ * asked of it runs kernel 2).
+ * All kernels produce identical results for the outputs they write; "automatic" never picks 4, 6 or 7 (measured slower). */
 int merlin_set_kernel_choice(int choice);
 /* Tuning/testing knob, process-wide DEFAULT for handles without their own setting: how gen_obs is computed.  0 = automatic (default): the symbolic-only kernel works
  * on seven window cells per 64-bit register (csrc/obs_swar.cuh; grids at least 7 wide), the frame kernels cell by cell

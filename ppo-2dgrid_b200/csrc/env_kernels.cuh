@@ -13,9 +13,11 @@ constexpr int kThreads = 256;                 // 8 warps per CTA
 #ifndef MERLIN_AUTO_RGB_CHOICE
 #define MERLIN_AUTO_RGB_CHOICE(N, SMS) ((N) <= 24576 ? 2 : 3)
 #endif
-// automatic choice 2 becomes 7 (env_kernel_quad) where that kernel applies: three actions, no shaping wrapper, RGB frames
+// Would the automatic choice 2 become 7 (env_kernel_quad) at N envs?  Measured and NOT adopted: under CUDA-graph replay
+// it is 7 % faster at 8192 envs (14.6 vs 15.7 us), equal at 5120-6144, slower below (8.8 vs 8.3 us at 4096) and above
+// (22.4 vs 20.6 us at 12 288), and slower everywhere when launched eagerly (profiles/r02_quad_vs_warp.txt).
 #ifndef MERLIN_AUTO_QUAD
-#define MERLIN_AUTO_QUAD(N) ((N) >= 6144 && (N) <= 12288)
+#define MERLIN_AUTO_QUAD(N) 0
 #endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kAtlasBytes = kAtlasTiles * kTileBytes;   // 24576

@@ -72,58 +72,76 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
 }
 
 // Small rollouts (a few thousand envs: one warp or less per SM in the kernel above, whose run time is then T / kChunk
-// dependent memory round trips plus the chain): a CTA owns 32 envs and a window of TC time steps at once.
-//   phase 1  ALL warps load the window's rew / val / done rows (every load of the window in flight together) and
-//            compute what does not depend on the scan -- delta[t] and c[t] = (gamma * lam) * mask[t] -- into shared memory;
-//   phase 2  ONE warp (lane = env) runs the recurrence gae = delta[t] + c[t] * gae from shared memory: two dependent
-//            fp32 operations per step;
-//   phase 3  ALL warps write adv[t] and ret[t] = val[t] + adv[t], coalesced.
+// dependent memory round trips plus the chain): a CTA of 8 warps owns 32 envs and a window of 128 time steps at once.
+//   phase 1  ALL warps load the window's rew / val / done rows -- 16 rows per warp, every load of the window in flight
+//            together -- and compute what does not depend on the scan, delta[t] and c[t] = (gamma * lam) * mask[t],
+//            into shared memory;
+//   phase 2  ONE warp (lane = env) runs the recurrence gae = delta[t] + c[t] * gae from shared memory, 16 steps per
+//            batch of shared-memory reads: two dependent fp32 operations per step; adv[t] and ret[t] = val[t] + adv[t]
+//            leave from there as coalesced 128-byte stores.
 // Same operations in the same order as gae_kernel (and the reference loop): bit-identical results.
+constexpr int kGaeRows = 16;                 // rows per warp per window (phase 1), steps per batch (phase 2)
+constexpr int kGaeWindow = 8 * kGaeRows;     // 128 time steps x 32 envs x 3 arrays x 4 B = 48 KB of shared memory
 __global__ void __launch_bounds__(256) gae_tile_kernel(const float* __restrict__ rew, const float* __restrict__ val,
                                                        const float* __restrict__ done, const float* __restrict__ last_val,
                                                        float* __restrict__ adv, float* __restrict__ ret, const int T,
-                                                       const int N, const int TC, const double gamma, const float g32,
-                                                       const float gl32) {
-  extern __shared__ float sm[];
-  float* s_delta = sm;                 // [TC][32]
-  float* s_c = sm + TC * 32;           // [TC][32]
-  float* s_a = sm + 2 * TC * 32;       // [TC][32]   (3 x 128 x 32 floats = 48 KB: no opt-in needed)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                                                       const int N, const double gamma, const float g32, const float gl32) {
+  __shared__ float s_delta[kGaeWindow * 32], s_c[kGaeWindow * 32], s_v[kGaeWindow * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
   const bool ok = n < N;
   float gae = 0.f;
-  for (int t_hi = T - 1; t_hi >= 0; t_hi -= TC) {
-    const int len = min(TC, t_hi + 1), t_lo = t_hi - len + 1;
+  for (int t_hi = T - 1; t_hi >= 0; t_hi -= kGaeWindow) {
+    const int len = min(kGaeWindow, t_hi + 1), t_lo = t_hi - len + 1;
     if (ok) {
-      for (int j = w; j < len; j += nw) {
-        const int t = t_lo + j;
-        const size_t k = (size_t)t * N + n;
-        const float r = rew[k], v = val[k], d = done[k];
-        // gamma * next_val: python double product rounded to f32 at t = T-1, else gamma(f32) * values[t+1]
-        const float gnext = t == T - 1 ? (float)(gamma * (double)last_val[n]) : __fmul_rn(g32, val[k + N]);
-        const float mask = __fsub_rn(1.0f, d);
-        s_delta[j * 32 + lane] = __fsub_rn(__fadd_rn(r, __fmul_rn(gnext, mask)), v);
-        s_c[j * 32 + lane] = __fmul_rn(gl32, mask);
+      float r[kGaeRows], v[kGaeRows], d[kGaeRows], vn[kGaeRows];
+#pragma unroll
+      for (int i = 0; i < kGaeRows; ++i) {       // rows j = w + 8 i of the window
+        const int j = w + 8 * i, t = t_lo + j;
+        if (j < len) {
+          const size_t k = (size_t)t * N + n;
+          r[i] = rew[k]; v[i] = val[k]; d[i] = done[k];
+          vn[i] = t == T - 1 ? 0.f : val[k + N];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kGaeRows; ++i) {
+        const int j = w + 8 * i, t = t_lo + j;
+        if (j < len) {
+          // gamma * next_val: python double product rounded to f32 at t = T-1, else gamma(f32) * values[t+1]
+          const float gnext = t == T - 1 ? (float)(gamma * (double)last_val[n]) : __fmul_rn(g32, vn[i]);
+          const float mask = __fsub_rn(1.0f, d[i]);
+          s_delta[j * 32 + lane] = __fsub_rn(__fadd_rn(r[i], __fmul_rn(gnext, mask)), v[i]);
+          s_c[j * 32 + lane] = __fmul_rn(gl32, mask);
+          s_v[j * 32 + lane] = v[i];
+        }
       }
     }
     __syncthreads();
     if (w == 0 && ok) {
-#pragma unroll 8
-      for (int j = len - 1; j >= 0; --j) {
-        gae = __fadd_rn(s_delta[j * 32 + lane], __fmul_rn(s_c[j * 32 + lane], gae));
-        s_a[j * 32 + lane] = gae;
+      int j = len - 1;
+      for (; j >= kGaeRows - 1; j -= kGaeRows) {
+        float dl[kGaeRows], c[kGaeRows], v[kGaeRows];
+#pragma unroll
+        for (int i = 0; i < kGaeRows; ++i) {
+          dl[i] = s_delta[(j - i) * 32 + lane]; c[i] = s_c[(j - i) * 32 + lane]; v[i] = s_v[(j - i) * 32 + lane];
+        }
+#pragma unroll
+        for (int i = 0; i < kGaeRows; ++i) {
+          const size_t k = (size_t)(t_lo + j - i) * N + n;
+          gae = __fadd_rn(dl[i], __fmul_rn(c[i], gae));
+          adv[k] = gae;
+          ret[k] = __fadd_rn(v[i], gae);
+        }
       }
-    }
-    __syncthreads();
-    if (ok) {
-      for (int j = w; j < len; j += nw) {
+      for (; j >= 0; --j) {
         const size_t k = (size_t)(t_lo + j) * N + n;
-        const float a = s_a[j * 32 + lane];
-        adv[k] = a;
-        ret[k] = __fadd_rn(val[k], a);   // second read of the row: L1 / L2
+        gae = __fadd_rn(s_delta[j * 32 + lane], __fmul_rn(s_c[j * 32 + lane], gae));
+        adv[k] = gae;
+        ret[k] = __fadd_rn(s_v[j * 32 + lane], gae);
       }
     }
-    __syncthreads();   // the next window overwrites s_a
+    __syncthreads();   // the next window overwrites the shared arrays
   }
 }
 
@@ -135,10 +153,8 @@ cudaError_t launch_gae(const float* rew, const float* val, const float* done, co
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream) {
   // small rollouts: 32-thread blocks spread the envs over more SMs (4096 envs -> 128 blocks instead of 32)
   if (N <= MERLIN_GAE_TILE_MAX_ENVS) {
-    const int TC = T < 128 ? (T < 1 ? 1 : T) : 128;
-    const size_t smem = (size_t)3 * TC * 32 * sizeof(float);
-    gae_tile_kernel<<<(N + 31) / 32, 256, smem, stream>>>(rew, val, done, last_val, adv, ret, T, N, TC, gamma, (float)gamma,
-                                                          (float)(gamma * lam));
+    gae_tile_kernel<<<(N + 31) / 32, 256, 0, stream>>>(rew, val, done, last_val, adv, ret, T, N, gamma, (float)gamma,
+                                                       (float)(gamma * lam));
     return cudaGetLastError();
   }
   const bool large = N >= 32768;

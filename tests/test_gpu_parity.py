@@ -16,12 +16,10 @@ from oracle import fast
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[1, 2, 3, 7], ids=["group_kernel", "warp_kernel", "tile_kernel", "quad_kernel"])
+@pytest.fixture(autouse=True, params=[1, 2, 3], ids=["group_kernel", "warp_kernel", "tile_kernel"])
 def kernel_choice(request):
-    """Every parity test runs against all four production step kernels (warp owns a group / warp per env / CTA tile /
-    four envs per warp -- the last serves steps of the three-action configuration and hands everything else to the
-    warp-per-env kernel); the two
-    measured-and-not-adopted mappings (TMA frame stores, ordered groups) have tests/test_gpu_variants.py."""
+    """Every parity test runs against all three step kernels (warp owns a group / warp per env / CTA tile); the three
+    measured-and-not-adopted mappings (TMA frame stores, ordered groups, four envs per warp) have tests/test_gpu_variants.py."""
     from merlin_b200 import set_kernel_choice
     set_kernel_choice(request.param)
     yield request.param

@@ -1,6 +1,8 @@
-"""Parity of the two selectable step-kernel mappings that were measured and not adopted as defaults: the CTA-tile kernel
+"""Parity of the selectable step-kernel mappings that were measured and not adopted as defaults: the CTA-tile kernel
 with the frame phase routed through the TMA unit (choice 4: frames assembled in shared memory, one 9408-byte
-cp.async.bulk per frame) and the group kernel with groups handed out in order (choice 6).  Same bar as every other
+cp.async.bulk per frame), the group kernel with groups handed out in order (choice 6) and the kernel that serves four
+envs per warp, eight lanes each (choice 7: steps of the three-action configuration; everything else asked of it runs
+the warp-per-env kernel).  Same bar as every other
 mapping: bit-exact observations, rewards, flags, poses and grids against the oracle and the reference fixtures."""
 import os
 import sys
@@ -14,8 +16,8 @@ import helpers  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[(4, 0), (6, 0), (3, 2), (6, 2)],
-                ids=["tile_tma_kernel", "ordered_kernel", "tile_kernel_row_obs", "ordered_kernel_row_obs"])
+@pytest.fixture(autouse=True, params=[(4, 0), (6, 0), (7, 0), (3, 2), (6, 2)],
+                ids=["tile_tma_kernel", "ordered_kernel", "quad_kernel", "tile_kernel_row_obs", "ordered_kernel_row_obs"])
 def kernel_choice(request):
     """(kernel choice, observation path): path 2 = the row-parallel gen_obs (obs_swar.cuh) in kernels that default to the
     per-cell form (the symbolic-only kernel uses it by default and is covered by the main suites)."""
@@ -48,6 +50,31 @@ def test_random_rollouts_vs_oracle(N):
     tp._compare_batched(N, enc, agent, 60 if N < 2000 else 12, max_steps=25, seed=N)
     tp._compare_batched(N, enc, agent, 30 if N < 2000 else 8, max_steps=25, seed=N + 1, stuck_penalty=True,
                         exploration_bonus=0.01)
+
+
+@pytest.mark.parametrize("N", [2, 5, 6, 7, 4097, 6000, 20000])
+def test_ragged_quads_and_many_restarts(N):
+    """Batch sizes that leave the last group of four envs ragged, one-round and multi-round launch shapes, short episodes
+    (most steps restart some env onto another layout)."""
+    tp = _parity()
+    _, codes, _, layouts, _ = tp._mods()
+    cells, agent = layouts.generate("mediumhard", 16, range(5000, 5257))
+    enc = codes.unpack_to_encoding(cells, 16, 16)
+    _, _, n_done = tp._compare_batched(N, enc, agent, 40 if N < 5000 else 16, max_steps=7, seed=N,
+                                       check_every=1 if N < 5000 else 5)
+    assert n_done > 0
+
+
+@pytest.mark.parametrize("W,H,N", [(3, 3, 41), (5, 12, 97), (19, 7, 97), (255, 255, 66), (255, 4, 65)])
+def test_grid_extents(W, H, N):
+    """3x3 (every window mostly outside the grid) to 255x255, W != H; doors and keys in a three-action pool (opaque
+    closed / locked doors, Grid.encode's state byte)."""
+    tp = _parity()
+    rng = np.random.default_rng(W * 1000 + H)
+    enc, agent = tp._rect_layouts(rng, 24 if W * H < 10000 else 6, W, H)
+    tp._compare_batched(N, enc, agent, 40, max_steps=13, seed=W + H)
+    enc, agent = tp._object_layouts(rng, 48, 11)
+    tp._compare_batched(203, enc, agent, 40, max_steps=17, seed=W)
 
 
 def test_symbolic_only_kernel_per_cell_and_row_forms_agree():

@@ -32,7 +32,7 @@ def main():
     except Exception:
         peak = 6650.0
     rows = []
-    for T, N in [(2048, 1), (128, 4096), (128, 65536), (128, 524288), (1024, 65536), (64, 1048576), (256, 1048576)]:
+    for T, N in [(2048, 1), (128, 32), (128, 1024), (128, 4096), (128, 16384), (128, 65536), (128, 524288), (1024, 65536), (64, 1048576), (256, 1048576)]:
         rew = torch.rand(T, N, device=dev)
         val = torch.randn(T, N, device=dev)
         done = (torch.rand(T, N, device=dev) < 0.01).float()
@@ -63,6 +63,31 @@ def main():
         nbytes = 20 * T * N + 4 * N
         rows.append({"T": T, "N": N, "ms": ms, "algorithmic_mb": nbytes / 1e6, "achieved_gbs": nbytes / ms / 1e6,
                      "frac_of_hbm_peak": nbytes / ms / 1e6 / peak})
+        if big is not None:
+            # small rollouts: an event pair around ONE launch carries several microseconds of its own; 32 calls replayed
+            # from a CUDA graph give the kernel's own time (inputs L2-resident, as they are right after a rollout)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                sptr = side.cuda_stream
+                for _ in range(2):
+                    _lib.check(lib.merlin_gae(rew.data_ptr(), val.data_ptr(), done.data_ptr(), last.data_ptr(),
+                                              adv.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95, sptr))
+                side.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(32):
+                        _lib.check(lib.merlin_gae(rew.data_ptr(), val.data_ptr(), done.data_ptr(), last.data_ptr(),
+                                                  adv.data_ptr(), ret.data_ptr(), T, N, 0.99, 0.95, sptr))
+            graph.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(4):
+                graph.replay()
+            g1.record()
+            torch.cuda.synchronize()
+            rows[-1]["us_per_call_cuda_graph_l2_warm"] = g0.elapsed_time(g1) / 128 * 1e3
         print(json.dumps(rows[-1]), flush=True)
         del rew, val, done, last
     # the reference loop (0-dim torch tensors, CPU) on one env, T = 2048
