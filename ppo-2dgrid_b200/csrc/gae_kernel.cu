@@ -145,14 +145,18 @@ __global__ void __launch_bounds__(256) gae_tile_kernel(const float* __restrict__
   }
 }
 
+// Where the tile kernel runs.  32 calls replayed from a CUDA graph, L2-warm (tools/bench_gae.py, T = 128), tile kernel vs
+// one thread per env: 6.06 vs 5.61 us at 32 envs (one CTA: nothing to spread), 6.06 vs 7.57 at 1024, 6.14 vs 7.61 at 4096,
+// 12.2 vs 11.8 at 16 384 (512 CTAs of 48 KB: four rounds per SM).
 #ifndef MERLIN_GAE_TILE_MAX_ENVS
-#define MERLIN_GAE_TILE_MAX_ENVS 16384   // up to here the tile kernel runs (<= 512 CTAs); above, one thread per env
+#define MERLIN_GAE_TILE_MIN_ENVS 128
+#define MERLIN_GAE_TILE_MAX_ENVS 8192
 #endif
 
 cudaError_t launch_gae(const float* rew, const float* val, const float* done, const float* last_val, float* adv,
                        float* ret, int T, int N, double gamma, double lam, cudaStream_t stream) {
   // small rollouts: 32-thread blocks spread the envs over more SMs (4096 envs -> 128 blocks instead of 32)
-  if (N <= MERLIN_GAE_TILE_MAX_ENVS) {
+  if (N >= MERLIN_GAE_TILE_MIN_ENVS && N <= MERLIN_GAE_TILE_MAX_ENVS) {
     gae_tile_kernel<<<(N + 31) / 32, 256, 0, stream>>>(rew, val, done, last_val, adv, ret, T, N, gamma, (float)gamma,
                                                        (float)(gamma * lam));
     return cudaGetLastError();

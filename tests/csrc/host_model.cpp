@@ -117,6 +117,8 @@ int hm_sample(int N, int n_actions, const float* logits, uint64_t seed, const ui
 // Grid.process_vis on a 49-bit transparency mask (bit vj*7 + vi), for the property tests.
 unsigned long long hm_visibility(unsigned long long transp) { return merlin::visibility(transp); }
 unsigned long long hm_visibility_literal(unsigned long long transp) { return merlin::visibility_literal(transp); }
+// The byte-per-row form env_kernel_quad's lanes exchange (row vj in bits 8*vj .. 8*vj+6, in and out).
+unsigned long long hm_visibility_rows(unsigned long long transp_rows) { return merlin::visibility_rows(transp_rows); }
 // One process_vis row, both forms: returns lit | next_seed << 8.
 unsigned hm_vis_row(unsigned seed, unsigned T, int literal) {
   uint32_t lit = 0;

@@ -245,6 +245,13 @@ def test_visibility_row_carry_chain_form_equals_literal_sweeps_exhaustively():
         for _ in range(5000):
             m = int(sum(1 << i for i in np.nonzero(rng.random(49) < dens)[0]))
             assert lib.hm_visibility(m) == lib.hm_visibility_literal(m), m
+    # the byte-per-row form (env_kernel_quad): same rows in, same rows out
+    lib.hm_visibility_rows.restype = ctypes.c_uint64
+    lib.hm_visibility_rows.argtypes = [ctypes.c_uint64]
+    spread = lambda m: sum(((m >> (7 * vj)) & 0x7f) << (8 * vj) for vj in range(7))
+    for _ in range(5000):
+        m = int(sum(1 << i for i in np.nonzero(rng.random(49) < 0.7)[0]))
+        assert lib.hm_visibility_rows(spread(m)) == spread(lib.hm_visibility(m)), m
 
 
 # ---- in-kernel action sampler (env_logic.cuh: Philox4x32-10, inverse CDF) -------------------------------------

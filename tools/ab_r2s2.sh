@@ -1,5 +1,9 @@
-# development aid (round 2, session 2): GAE tile kernel, quad-kernel variant tests (1 GPU)
-python -m pytest tests/test_gpu_parity.py -x -q -k "gae" > gpurun_out/s2_pytest.log 2>&1; tail -3 gpurun_out/s2_pytest.log
-python -m pytest tests/test_gpu_variants.py -x -q -k "quad" > gpurun_out/s2_pytest2.log 2>&1; tail -3 gpurun_out/s2_pytest2.log
-python tools/bench_gae.py --out gpurun_out/r02_gae_1gpu.json 2>&1 | tail -12
+# development aid (round 2, session 2): final validation + measurement pass (1 GPU)
+python -m pytest tests -q -m gpu > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu_steps20.json 2> gpurun_out/r02_bench_1gpu_steps20.err; tail -2 gpurun_out/r02_bench_1gpu_steps20.err
+python bench.py > gpurun_out/r02_bench_1gpu_default.json 2> gpurun_out/r02_bench_1gpu_default.err; tail -2 gpurun_out/r02_bench_1gpu_default.err
+python tools/sweep.py --out gpurun_out/r02_sweep_1gpu.json --sizes 4096,8192,16384,24576,65536,262144,1048576 --compact 2>&1 | grep N=
+python tools/bench_gae.py --out gpurun_out/r02_gae_1gpu.json 2>&1 | cut -c1-230 | tail -12
+MERLIN_B200_LIB=$PWD/ppo-2dgrid_b200/lib/variants/lib_gae_old.so python tools/bench_gae.py --out gpurun_out/r02_gae_1gpu_thread_per_env.json 2>&1 | cut -c1-230 | head -6
 echo done
