@@ -1320,6 +1320,9 @@ constexpr int kF32Chunks = kImgBytes / 4;                  // 2352 float4 chunks
 constexpr int kF32Iters = (kF32Chunks + 31) / 32;          // 74
 constexpr int kRenderF32Group = 8;                          // frames per ticket: 301 KB, like the u8 kernels' groups
 constexpr int kRenderF32Threads = 256;
+#ifndef MERLIN_RENDER_F32_CTA_FRAMES_MAX
+#define MERLIN_RENDER_F32_CTA_FRAMES_MAX 8192
+#endif
 
 __host__ __device__ constexpr size_t render_f32_smem(int cap_tiles) {
   return (size_t)cap_tiles * kTileBytes * 4 + 128 + 592 * 2 + (kRenderF32Threads / 32) * 128;
@@ -1440,9 +1443,13 @@ cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t 
   }
   const int per_sm = smem > 72 * 1024 ? 2 : 3;
   RenderParams q = p;
-  // fewer frames than resident CTAs: one CTA per frame (no ticket counter involved), else groups of 8 frames per ticket
-  q.frame_per_cta = p.M <= sm_count * per_sm ? 1 : 0;
-  const int grid = q.frame_per_cta ? p.M : min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
+  // Few frames -- up to a few rounds of (resident CTAs x 8 warps): a CTA renders a frame with all its warps and strides
+  // over the frames (no ticket counter involved).  With a warp per frame, 4096 frames are 1.15 rounds of the 3552 resident
+  // warps, i.e. two rounds of which the second is 15 % full; with a CTA per frame they are 9.2 rounds of 444 CTAs, i.e. ten.
+  // Above: groups of 8 frames per ticket, one warp per frame.
+  q.frame_per_cta = p.M <= MERLIN_RENDER_F32_CTA_FRAMES_MAX ? 1 : 0;
+  const int grid = q.frame_per_cta ? min(p.M, sm_count * per_sm)
+                                   : min(sm_count * per_sm, (p.M + kRenderF32Group - 1) / kRenderF32Group);
   render_f32_kernel<<<grid, kRenderF32Threads, smem, stream>>>(q);
   return cudaGetLastError();
 }

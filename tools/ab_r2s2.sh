@@ -1,9 +1,10 @@
-# development aid (round 2, session 2): final validation + measurement pass (1 GPU)
-python -m pytest tests -q -m gpu > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu_steps20.json 2> gpurun_out/r02_bench_1gpu_steps20.err; tail -2 gpurun_out/r02_bench_1gpu_steps20.err
-python bench.py > gpurun_out/r02_bench_1gpu_default.json 2> gpurun_out/r02_bench_1gpu_default.err; tail -2 gpurun_out/r02_bench_1gpu_default.err
-python tools/sweep.py --out gpurun_out/r02_sweep_1gpu.json --sizes 4096,8192,16384,24576,65536,262144,1048576 --compact 2>&1 | grep N=
-python tools/bench_gae.py --out gpurun_out/r02_gae_1gpu.json 2>&1 | cut -c1-230 | tail -12
-MERLIN_B200_LIB=$PWD/ppo-2dgrid_b200/lib/variants/lib_gae_old.so python tools/bench_gae.py --out gpurun_out/r02_gae_1gpu_thread_per_env.json 2>&1 | cut -c1-230 | head -6
+# development aid (round 2, session 2): render_f32 launch modes at small / mid frame counts (1 GPU)
+V=$PWD/ppo-2dgrid_b200/lib/variants
+for v in rf_old default rf_32k; do
+  echo "== variant $v"
+  if [ $v = default ]; then unset MERLIN_B200_LIB; else export MERLIN_B200_LIB=$V/lib_$v.so; fi
+  python tools/bench_render.py --out gpurun_out/r02_render_$v.json 2>&1 | grep "render_f32 blocked'" | cut -c1-260
+done 2>&1 | tee gpurun_out/s2_render_ab.txt
+unset MERLIN_B200_LIB
+python -m pytest tests/test_gpu_parity.py -x -q -k "render" 2>&1 | tail -2
 echo done
