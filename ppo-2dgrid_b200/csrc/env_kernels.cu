@@ -711,11 +711,13 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// env_kernel_warp<STEP>: one WARP per environment -- the small-batch mapping (N <= 24 576: every env of the batch is
-// resident at once and the run time is launch latency + one env's dependent chain + the instructions issued per SM).
+// env_kernel_warp<STEP, PDL, LEAN>: one WARP per environment -- the small-batch mapping (N <= 24 576: every env of the
+// batch is resident at once or nearly so, and the run time is launch latency + one env's dependent chain + its stores).
 //   * state / action / forward cell are loaded at warp-uniform addresses (one broadcast transaction each) and the
 //     step logic runs redundantly on all lanes; lane 0 alone writes the per-env outputs and the new state.  The first
 //     env's state and action are requested BEFORE the atlas is staged, so both round trips overlap.
+//   * LEAN (three actions, no shaping wrapper => immutable grids; launch_warp_kernel): the step needs TWO dependent
+//     round trips instead of three -- see the block at `if (LEAN)`.
 //   * the 49-cell window is gathered two cells per lane; transparency goes through two warp ballots into the same
 //     49-bit mask the visibility routine consumes; every lane then knows the visibility of its own cells.
 //   * frame phase without a blit map: the frame is 28 pairs of pixel rows; a pair is 336 bytes = 21 16-byte chunks, and
@@ -723,7 +725,7 @@ static cudaError_t launch_sym_kernel(const EnvParams& p, const LaunchCtx& ctx, c
 //     pairs, its two (vi, part) are loop constants, the tile row (vj, py) is the loop counter, and after unrolling
 //     every shared-memory and global address is `lane register + immediate`: 3 instructions per chunk (two 8-byte
 //     atlas reads, one 16-byte store) plus 4 per tile row for the two kinds, ~115 per frame instead of ~480 with the
-//     588-entry chunk map (ncu at 4096 envs, profiles/r02_warp_kernel_ncu.md: 1390 -> ~650 warp instructions per env).
+//     588-entry chunk map (ncu at 4096 envs, profiles/r02_warp_n4096_v2_ncu_details.csv: 1387 -> 791 warp instructions per env).
 //     The kinds are kept premultiplied (kind * 192, the tile's byte offset in the atlas) as 16-bit words.
 //   * atlas staging touches only the slots the pool can show: thread t tests tile t / 2 and copies half of it.
 #ifndef MERLIN_WARP_THREADS
@@ -1006,12 +1008,15 @@ __global__ void __launch_bounds__(kWarpKernelThreads, MERLIN_WARP_CTAS) env_kern
 }
 
 // ---------------------------------------------------------------------------------------------------
-// env_kernel_quad<STEP>: one warp per FOUR environments, eight lanes per env -- the small-batch mapping for the
-// reference's own configuration (ThreeActionWrapper => immutable grids, no reward-shaping wrapper; RGB frames).
-// In env_kernel_warp one instruction stream serves one env and every lane repeats the warp-uniform step logic: at 4096
-// envs its ~620 state-phase instructions per env, on seven warps per scheduler that are all in the same phase, are 2.3 us
-// of issue time before the first frame byte leaves the SM (profiles/r02_warp_n4096_v3_ncu.md).  Here one stream serves
-// four envs -- everything below is uniform within a group of eight lanes and differs between the groups:
+// env_kernel_quad<STEP> (kernel choice 7): one warp per FOUR environments, eight lanes per env -- a small-batch mapping
+// for the reference's own configuration (ThreeActionWrapper => immutable grids, no reward-shaping wrapper; RGB frames).
+// MEASURED AND NOT ADOPTED as a default (profiles/r02_quad_vs_warp.txt): it executes 328 instead of 773 instructions per
+// env, but the small-batch step is bound by the latency of one env's dependent chain, not by issue slots (ncu at 4096
+// envs: env_kernel_warp 33 % of the issue slots busy, 15.8 cycles per issued instruction per warp) -- fewer, longer-
+// running warps hide less of it: 8.8 vs 8.3 us per step at 4096 envs, 22.4 vs 20.6 at 12 288, faster only around 8192
+// (14.6 vs 15.7).  Kept selectable and held to the parity bar (tests/test_gpu_variants.py).
+// In env_kernel_warp one instruction stream serves one env and every lane repeats the warp-uniform step logic.  Here one
+// stream serves four envs -- everything below is uniform within a group of eight lanes and differs between the groups:
 //   * lane r of a group loads ROW r of the 8-row x 7-column region in front of the agent's old cell (seven byte loads,
 //     all in flight together with the other rows'): both candidate windows -- the agent stays, or moves one cell ahead --
 //     lie inside it, so the step needs two dependent round trips (state + action, then cells), and the cell ahead is
