@@ -1251,8 +1251,10 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const RenderParams p) {
   for (int k = 0; k < kChunksPerLane; ++k) lut[k] = __ldg(p.lut + k * 32 + lane);
   __syncthreads();
 
-  // groups of kRenderGroup consecutive frames are drawn in order from a ticket counter (see env_kernel_tile)
-  constexpr int kRenderGroup = 32;
+  // groups of consecutive frames are drawn in order from a ticket counter (see env_kernel_tile): 32 frames per ticket
+  // for large batches (the write fronts of all CTAs stay in one narrow window), 8 -- one per warp -- for minibatch-sized
+  // ones (16 384 frames are 512 groups of 32 on 296 CTAs: two rounds, the second 73 % full; 2048 groups of 8 are 6.9)
+  const int kRenderGroup = p.group_frames;
   __shared__ int s_next;
   const int n_groups = (p.M + kRenderGroup - 1) / kRenderGroup;
   if (threadIdx.x == 0) s_next = (int)atomicAdd(&p.sched[0], 1u);
@@ -1300,13 +1302,18 @@ __global__ void __launch_bounds__(256, 2) render_kernel(const RenderParams p) {
   }
 }
 
+#ifndef MERLIN_RENDER_GROUP32_MIN_FRAMES
+#define MERLIN_RENDER_GROUP32_MIN_FRAMES 65536
+#endif
 cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
   constexpr int threads = 256, warps = threads / 32;
   const size_t smem = kAtlasBytes + warps * kWarpKindStride;
-  const int grid = min(sm_count * 2, (p.M + warps - 1) / warps);
-  if (blocked) render_kernel<true><<<grid, threads, smem, stream>>>(p);
-  else render_kernel<false><<<grid, threads, smem, stream>>>(p);
+  RenderParams q = p;
+  q.group_frames = p.M >= MERLIN_RENDER_GROUP32_MIN_FRAMES ? 32 : warps;
+  const int grid = min(sm_count * 2, (p.M + q.group_frames - 1) / q.group_frames);
+  if (blocked) render_kernel<true><<<grid, threads, smem, stream>>>(q);
+  else render_kernel<false><<<grid, threads, smem, stream>>>(q);
   return cudaGetLastError();
 }
 
@@ -1701,6 +1708,10 @@ static cudaError_t launch_quad_kernel(const EnvParams& p, const LaunchCtx& ctx, 
   return launch_maybe_pdl(env_kernel_quad<STEP, false>, false, grid, threads, smem, stream, p);
 }
 
+// tiles of 16 envs from this batch size up, tiles of 8 below
+#ifndef MERLIN_TILE16_MIN_ENVS
+#define MERLIN_TILE16_MIN_ENVS(SMS) ((SMS) * kTileCtasPerSm * 16)
+#endif
 constexpr int kSymWarpMaxEnvs = 2048;   // symbolic-only batches up to this size run the warp-per-env kernel
 
 template <int STEP>
@@ -1728,7 +1739,7 @@ static cudaError_t launch_sized(const EnvParams& p, const LaunchCtx& ctx, cudaSt
   }
   if (choice == 3) {
     // tiles of 16 envs once every resident CTA gets one; smaller tiles spread a small batch over more CTAs
-    if (p.N >= sm_count * kTileCtasPerSm * 16) return launch_tile_kernel<16, STEP>(p, ctx, stream);
+    if (p.N >= MERLIN_TILE16_MIN_ENVS(sm_count)) return launch_tile_kernel<16, STEP>(p, ctx, stream);
     return launch_tile_kernel<8, STEP>(p, ctx, stream);
   }
   // pick the largest group size that still yields >= ~8 warps per SM; tiny batches use smaller groups
@@ -1755,7 +1766,7 @@ const char* step_kernel_name(int n_envs, bool rgb, bool quad_ok, const LaunchCtx
   if (choice == 4) return "merlin::env_kernel_tile_tma<true>";
   if (choice == 6) return "merlin::env_kernel_ordered<true>";
   if (choice == 3)
-    return n_envs >= sm_count * kTileCtasPerSm * 16 ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>";
+    return n_envs >= MERLIN_TILE16_MIN_ENVS(sm_count) ? "merlin::env_kernel_tile<16,true>" : "merlin::env_kernel_tile<8,true>";
   const long long want_warps = (long long)sm_count * 8;
   if (n_envs / 32 >= want_warps) return "merlin::env_kernel<32,true>";
   if (n_envs / 16 >= want_warps) return "merlin::env_kernel<16,true>";

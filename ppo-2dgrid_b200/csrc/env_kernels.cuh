@@ -117,6 +117,7 @@ struct RenderParams {
   int normalise;             // 0: the pixel value; 1: pixel / 255.0f (IEEE division); 2: pixel * (1.0f / 255.0f)
   int cap_tiles;             // atlas slots the float atlas in shared memory can hold (8..128)
   int frame_per_cta;         // set by launch_render_f32: 1 = few frames, one CTA renders one frame with all its warps
+  int group_frames;          // set by launch_render: frames per work ticket of the u8 kernels
 };
 cudaError_t launch_render(const RenderParams& p, bool blocked, int sm_count, cudaStream_t stream);
 cudaError_t launch_render_f32(const RenderParams& p, int sm_count, cudaStream_t stream);

@@ -66,7 +66,7 @@ for M in (4096, 16384, 262144):
         if bytes_per_frame:
             row["algorithmic_GBps"] = M * bytes_per_frame / ms / 1e6
             row["frac_of_copy_peak"] = row["algorithmic_GBps"] / peak
-        if M <= 16384 and name.startswith("render_f32"):
+        if M <= 16384 and bytes_per_frame:
             # small launches: 16 calls replayed from a CUDA graph give the kernel's own time (no host gaps, L2-warm input)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
