@@ -222,7 +222,8 @@ def test_gae_bit_exact_on_reference_fixtures(tag):
     assert np.array_equal(_np(ret), fx[f"{tag}_ret_torch"])
 
 
-@pytest.mark.parametrize("T,N", [(128, 4096), (1, 5), (7, 33), (2048, 1), (9, 130), (15, 4097), (16, 5), (23, 75777)])
+@pytest.mark.parametrize("T,N", [(128, 4096), (1, 5), (7, 33), (2048, 1), (9, 130), (15, 4097), (16, 5), (23, 75777),
+                                 (300, 200), (129, 128), (256, 8192), (17, 8193)])   # tile kernel: several windows, range ends
 def test_gae_batched_vs_oracle(T, N):
     gae = _mods()[2]
     g = torch.Generator(device="cpu").manual_seed(T * 7 + N)
