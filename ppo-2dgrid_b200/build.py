@@ -19,6 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-extended-lambda",
     "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-I" + INCLUDE, "-I" + CSRC,
+    "--threads", "0",   # the translation units compile side by side (the step kernels are split over three of them)
 ]
 
 

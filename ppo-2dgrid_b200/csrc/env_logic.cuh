@@ -1,5 +1,5 @@
 // env_logic.cuh -- per-environment arithmetic of the MERLIN rollout hot path, written once as
-// host+device inline functions.  The CUDA kernels in env_kernels.cu call these per lane; the
+// host+device inline functions.  The CUDA kernels (env_kernels*.cu, render_kernels.cu) call these per lane; the
 // host-only model in tests/csrc/host_model.cpp compiles the SAME functions with g++ so the logic can
 // be checked against the oracle in the CPU test tier (it is a test vehicle, not a CPU fallback: the
 // product library exports no host compute path).

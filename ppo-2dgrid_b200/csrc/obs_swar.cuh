@@ -27,7 +27,7 @@ constexpr uint64_t kB01 = 0x0101010101010101ull;
 constexpr uint64_t kLow7 = 0x00ffffffffffffffull;                 // bytes 0..6
 constexpr uint64_t kWall7 = (kB01 * CODE_WALL) & kLow7;
 
-// Grid loads carry an L2 cache policy on the device (`pol`, from grid_policy() in env_kernels.cu: evict-last for the
+// Grid loads carry an L2 cache policy on the device (`pol`, from grid_policy() in env_kernels_common.cuh: evict-last for the
 // shared layout pool, which every step re-reads while gigabytes of observations stream through the same L2).
 MERLIN_HD uint64_t ld64(const uint8_t* p, uint64_t pol = 0) {
 #if defined(__CUDA_ARCH__)

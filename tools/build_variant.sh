@@ -10,5 +10,5 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$root/ppo-2dgrid_b200/lib/variants"
 cd "$root/ppo-2dgrid_b200"
 ${NVCC:-/usr/local/cuda/bin/nvcc} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-extended-lambda \
-  -shared -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../include -Icsrc "$@" -o "lib/variants/lib_$name.so" csrc/*.cu
+  -shared -Xcompiler -fPIC -ccbin /usr/bin/g++ --threads 0 -I../include -Icsrc "$@" -o "lib/variants/lib_$name.so" csrc/*.cu
 echo "$root/ppo-2dgrid_b200/lib/variants/lib_$name.so"
