@@ -65,3 +65,21 @@ def test_no_cpu_fallback(lib):
     rc = lib.merlin_gae(x.ctypes.data, x.ctypes.data, x.ctypes.data, x.ctypes.data, x.ctypes.data, x.ctypes.data,
                         4, 1, 0.99, 0.95, None)
     assert rc == _lib.ECUDA
+
+
+def test_tuning_knobs_validate_their_range(lib):
+    """The process-wide defaults of the two knobs need no device: every documented value is accepted, anything else is
+    MERLIN_EINVAL with a message, and the defaults end where they started (automatic)."""
+    from merlin_b200 import _lib
+    try:
+        for choice in range(0, 8):   # 0 automatic .. 7 four envs per warp (include/merlin_b200.h)
+            assert lib.merlin_set_kernel_choice(choice) == 0, choice
+        for bad in (-1, 8, 99):
+            assert lib.merlin_set_kernel_choice(bad) == _lib.EINVAL, bad
+            assert b"kernel choice" in lib.merlin_last_error()
+        for path in (0, 1, 2):
+            assert lib.merlin_set_observation_path(path) == 0, path
+        assert lib.merlin_set_observation_path(3) == _lib.EINVAL
+    finally:
+        lib.merlin_set_kernel_choice(0)
+        lib.merlin_set_observation_path(0)
