@@ -171,6 +171,37 @@ def test_batched_ppo_rollout_is_consistent_with_oracle_and_updates(graph):
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, agent.ac.parameters()))
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_batched_ppo_carries_unfinished_episodes_across_rollouts(graph):
+    """horizon < max_steps: a rollout continues the episodes the previous one left unfinished (carry_episodes, automatic
+    then) -- its first observation is the one the last rollout ended on, episode clocks run on across rollouts, episodes
+    longer than the horizon reach the log; with carry_episodes=False every rollout starts from a fresh reset()."""
+    from src.ppo import PPO
+    N, T, M = 64, 8, 20
+    torch.manual_seed(3)
+    env = _sc().create_batched_env("mediumhard", N, device="cuda:0", seeds=range(128), max_steps=M)
+    agent = PPO(env, batch_size=N * T, minibatch_size=128, update_epochs=1, use_cuda_graph=graph)
+    assert agent.carry_episodes
+    agent.collect_rollouts()
+    sc1 = env.state_numpy()["step_count"]
+    assert agent.unfinished_episodes == int((sc1 > 0).sum()) > 0 and sc1.max() == T
+    ended_on = agent._last_obs.clone()
+    agent.collect_rollouts()
+    assert torch.equal(agent.buffer.get()[0][0], ended_on)          # rollout 2 opens where rollout 1 stopped
+    sc2 = env.state_numpy()["step_count"]
+    assert sc2.max() == 2 * T and int((sc2 == 2 * T).sum()) >= int((sc1 == T).sum()) // 2
+    agent.collect_rollouts()                                         # 24 steps > max_steps 20: truncations at 20
+    assert max(agent.episode_lengths) == M > T
+    assert env.state_numpy()["step_count"].max() < M
+    torch.manual_seed(3)
+    env2 = _sc().create_batched_env("mediumhard", N, device="cuda:0", seeds=range(128), max_steps=M)
+    fresh = PPO(env2, batch_size=N * T, minibatch_size=128, update_epochs=1, use_cuda_graph=graph, carry_episodes=False)
+    for _ in range(3):
+        fresh.collect_rollouts()
+        assert env2.state_numpy()["step_count"].max() == T         # every rollout restarted all envs
+    assert all(l <= T for l in fresh.episode_lengths)
+
+
 def test_batched_ppo_stored_logp_and_values_match_evaluate():
     from src.ppo import PPO
     torch.manual_seed(1)
